@@ -1,0 +1,138 @@
+/*
+ * torbi_b200 -- C ABI of the B200-native Viterbi decoder.
+ *
+ * This is the drop-in boundary for torbi's one hot path.  It replaces the
+ * PyTorch custom operator
+ *
+ *     torbi::viterbi_decode(Tensor observation, Tensor batch_frames,
+ *                           Tensor transition, Tensor initial) -> Tensor
+ *
+ * declared at /root/reference/torbi/csrc/ops.cpp:16-18 and implemented by
+ * viterbi_decode_cpu (/root/reference/torbi/csrc/viterbi.cpp:182-234) and
+ * viterbi_decode_cuda (/root/reference/torbi/csrc/cuda/viterbi.cu:309-362),
+ * whose only caller is torbi.decode (/root/reference/torbi/viterbi.py:53).
+ * The bindings a maintainer adds on the reference side are in INTEGRATION.md.
+ *
+ * Plain C: pointers and sizes only, no torch / ATen types.  Results follow the
+ * reference CPU operator exactly: decoded indices bit-exact, fp32 forward
+ * scores bit-exact (same add / max order), lowest source index wins ties
+ * (viterbi.cpp:94-101), first-occurrence final argmax (viterbi.cpp:218),
+ * positions t >= batch_frames[b]-1 hold the final state (viterbi.cpp:219-221).
+ *
+ * There is no CPU fallback: every entry point needs a CUDA device of compute
+ * capability 10.x and fails with TORBI_B200_ERR_CUDA otherwise.
+ */
+#ifndef TORBI_B200_H_
+#define TORBI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TORBI_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define TORBI_B200_API __attribute__((visibility("default")))
+#else
+#define TORBI_B200_API
+#endif
+
+/* status codes (0 = success, negative = failure; text via torbi_b200_last_error) */
+#define TORBI_B200_OK 0
+#define TORBI_B200_ERR_INVALID_ARGUMENT (-1) /* shapes, NULLs, frames outside [1,T], S > 65535 */
+#define TORBI_B200_ERR_WORKSPACE (-2)        /* workspace too small or misaligned            */
+#define TORBI_B200_ERR_CUDA (-3)             /* launch / runtime failure, no sm_100 device   */
+#define TORBI_B200_ERR_OUT_OF_MEMORY (-4)    /* host-entry arena could not be allocated      */
+
+/* flags: the log-space conversion torbi.from_probabilities applies on the host
+ * (/root/reference/torbi/core.py:189-197), fused into the forward kernel's
+ * observation load instead of three extra passes over (B,T,S). */
+#define TORBI_B200_OBS_IS_PROBABILITY (1u << 0) /* x <- logf(x) first (core.py:189-190)        */
+#define TORBI_B200_EPS_FLOOR (1u << 1)          /* x <- logf(expf(x) + FLT_MIN) (core.py:193-197) */
+/* kernel selection, for tests and profiling; default 0 lets the library pick */
+#define TORBI_B200_FORCE_GENERIC (1u << 8)      /* one CTA per sequence, any S                 */
+#define TORBI_B200_FORCE_TILED (1u << 9)        /* batch-tiled max-plus kernel                 */
+
+TORBI_B200_API int torbi_b200_abi_version(void);
+
+/* Thread-local description of the last failure on the calling thread. */
+TORBI_B200_API const char *torbi_b200_last_error(void);
+
+/* Number of CUDA devices usable by this library (compute capability 10.x). */
+TORBI_B200_API int torbi_b200_device_count(void);
+
+/* Bytes of device workspace torbi_b200_decode needs for this shape
+ * (uint16 backpointers B*T*S*2, ping-pong forward scores, scheduling state).
+ * Returns 0 on invalid shape. */
+TORBI_B200_API size_t torbi_b200_workspace_bytes(int64_t batch, int64_t frames, int64_t states, uint32_t flags);
+
+/*
+ * Decode a batch resident in device memory.  Replaces viterbi_decode_cuda
+ * (viterbi.cu:309-362); argument meaning follows viterbi.py:5-30.
+ *
+ *   observation   device (batch, frames, states) fp32, contiguous.  Log
+ *                 probabilities, or whatever `flags` says.  Never written.
+ *   batch_frames  HOST   (batch,) int32, each in [1, frames]  (the reference
+ *                 trusts these, viterbi.cpp:66; here they are validated)
+ *   transition    device (states, states) fp32 log-probs, [destination][source]
+ *                 (viterbi.cpp:83-84)
+ *   initial       device (states,) fp32 log-probs
+ *   indices       device (batch, frames) int32, output
+ *   posterior     device (batch, states) fp32 final forward scores, or NULL
+ *                 (the reference keeps these internal, viterbi.cpp:204-206)
+ *   workspace     device, >= torbi_b200_workspace_bytes(...), 256-byte aligned;
+ *                 owned by the caller, contents undefined afterwards
+ *   stream        cudaStream_t (NULL = legacy default stream).  All work is
+ *                 enqueued on it, on the CURRENT device; the call does not
+ *                 synchronise.
+ *
+ * The library never allocates or frees device memory in this entry point and
+ * is re-entrant across host threads (one per device).
+ */
+TORBI_B200_API int torbi_b200_decode(const float *observation, const int32_t *batch_frames,
+                      const float *transition, const float *initial, int64_t batch,
+                      int64_t frames, int64_t states, uint32_t flags, int32_t *indices,
+                      float *posterior, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Decode a batch resident in HOST memory on one device: host->device copies,
+ * decode and the device->host copy of the indices are all inside the call,
+ * which returns when `indices` is complete.  Pinned host buffers copy at full
+ * PCIe rate; pageable ones work too.  Device buffers come from a per-device
+ * arena the library grows on demand and keeps (torbi_b200_release frees it).
+ * This is the entry torbi.from_probabilities(gpu=k) uses for CPU tensors
+ * (/root/reference/torbi/core.py:147-191 moves them with .to(device)).
+ */
+TORBI_B200_API int torbi_b200_decode_host(const float *observation, const int32_t *batch_frames,
+                           const float *transition, const float *initial, int64_t batch,
+                           int64_t frames, int64_t states, uint32_t flags, int32_t *indices,
+                           float *posterior, int device);
+
+/*
+ * Same, sharding the independent batch items across several devices of one
+ * box (longest-processing-time-first by batch_frames; one host thread and one
+ * stream per device; no collective -- each device writes its own rows of the
+ * caller's `indices`).  devices[i] are CUDA ordinals; n_devices >= 1.
+ */
+TORBI_B200_API int torbi_b200_decode_host_multi(const float *observation, const int32_t *batch_frames,
+                                 const float *transition, const float *initial,
+                                 int64_t batch, int64_t frames, int64_t states,
+                                 uint32_t flags, int32_t *indices, float *posterior,
+                                 const int *devices, int n_devices);
+
+/* Free the host-entry arenas (all devices).  Safe to call at any time no decode
+ * is in flight. */
+TORBI_B200_API void torbi_b200_release(void);
+
+/* Counters for bench.py: kernels launched by this library since load, and the
+ * name of the forward kernel the last decode on this thread used. */
+TORBI_B200_API uint64_t torbi_b200_launch_count(void);
+TORBI_B200_API const char *torbi_b200_last_kernel(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TORBI_B200_H_ */

@@ -1,0 +1,83 @@
+"""ctypes binding of libtorbi_b200.so (include/torbi_b200.h).
+
+Replaces the `torch.ops.load_library(_C*.so)` discovery of
+/root/reference/torbi/__init__.py:24-59.  There is exactly one library, built
+in-tree by `make -C torbi_b200/csrc` (or __graft_entry__.build()); if it is
+missing every decode fails loudly -- there is no Python or CPU fallback.
+"""
+import ctypes
+import pathlib
+
+LIBRARY = pathlib.Path(__file__).resolve().parent / 'libtorbi_b200.so'
+
+OK = 0
+ERR_INVALID_ARGUMENT = -1
+ERR_WORKSPACE = -2
+ERR_CUDA = -3
+ERR_OUT_OF_MEMORY = -4
+
+OBS_IS_PROBABILITY = 1 << 0
+EPS_FLOOR = 1 << 1
+FORCE_GENERIC = 1 << 8
+FORCE_TILED = 1 << 9
+
+ABI_VERSION = 1
+
+_p = ctypes.c_void_p
+_i64 = ctypes.c_int64
+
+SIGNATURES = {
+    'torbi_b200_abi_version': (ctypes.c_int, []),
+    'torbi_b200_last_error': (ctypes.c_char_p, []),
+    'torbi_b200_device_count': (ctypes.c_int, []),
+    'torbi_b200_workspace_bytes': (ctypes.c_size_t, [_i64, _i64, _i64, ctypes.c_uint32]),
+    'torbi_b200_decode': (ctypes.c_int, [
+        _p, _p, _p, _p, _i64, _i64, _i64, ctypes.c_uint32, _p, _p, _p, ctypes.c_size_t, _p]),
+    'torbi_b200_decode_host': (ctypes.c_int, [
+        _p, _p, _p, _p, _i64, _i64, _i64, ctypes.c_uint32, _p, _p, ctypes.c_int]),
+    'torbi_b200_decode_host_multi': (ctypes.c_int, [
+        _p, _p, _p, _p, _i64, _i64, _i64, ctypes.c_uint32, _p, _p, _p, ctypes.c_int]),
+    'torbi_b200_release': (None, []),
+    'torbi_b200_launch_count': (ctypes.c_uint64, []),
+    'torbi_b200_last_kernel': (ctypes.c_char_p, []),
+}
+
+_lib = None
+
+
+def library():
+    """Load (once) and return the ctypes handle; raise if the build is absent."""
+    global _lib
+    if _lib is None:
+        if not LIBRARY.exists():
+            raise RuntimeError(
+                f'{LIBRARY} not found: build it with `make -C torbi_b200/csrc` '
+                '(or `python -c "import __graft_entry__ as g; g.build()"`). '
+                'torbi_b200 has no CPU or pure-Python decode path.')
+        lib = ctypes.CDLL(str(LIBRARY))
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if lib.torbi_b200_abi_version() != ABI_VERSION:
+            raise RuntimeError('libtorbi_b200.so ABI version mismatch; rebuild')
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return library().torbi_b200_last_error().decode()
+
+
+def check(status: int):
+    """Map a C status to the exception the reference would raise: bad shapes /
+    dtypes are ValueError, everything else RuntimeError (the reference raises
+    RuntimeError from TORCH_INTERNAL_ASSERT, viterbi.cpp:187-190)."""
+    if status == OK:
+        return
+    message = last_error()
+    if status == ERR_INVALID_ARGUMENT:
+        raise ValueError(f'torbi_b200: {message}')
+    if status == ERR_OUT_OF_MEMORY:
+        raise MemoryError(f'torbi_b200: {message}')
+    raise RuntimeError(f'torbi_b200: {message} (status {status})')

@@ -1,0 +1,441 @@
+"""Tensor API and file / batch drivers with the signatures of
+/root/reference/torbi/core.py:110-473, on top of the sm_100a decoder.
+
+Differences from the reference, all on purpose:
+  * no CPU / MPS path: `gpu=None` works only for CUDA inputs, else raises;
+  * `gpu` may also be a sequence of ordinals or 'all': independent items / files
+    are sharded across those GPUs, longest first, with no collective beyond
+    gathering the int32 index arrays;
+  * the log-space conversion of the observation (core.py:189-197) is fused into
+    the forward kernel instead of four elementwise passes, and the caller's
+    tensor is never mutated (the reference mutates it in place, core.py:195-197);
+    `conversion='host'` reproduces the reference's CPU torch ops exactly instead.
+"""
+import math
+import os
+import threading
+from typing import Dict, List, Optional, Sequence, Union
+
+import torch
+
+import torbi_b200
+from . import _ffi
+from .viterbi import decode
+
+__all__ = [
+    'from_probabilities', 'from_file', 'from_file_to_file', 'from_files_to_files',
+    'from_dataloader', 'save', 'save_masked']
+
+Gpu = Optional[Union[int, str, Sequence[int]]]
+
+
+###############################################################################
+# Device selection and sharding
+###############################################################################
+
+
+def _resolve_devices(gpu: Gpu, observation: Optional[torch.Tensor] = None) -> List[int]:
+    """`gpu` of the reference API (core.py:147-150) -> list of CUDA ordinals."""
+    if isinstance(gpu, str):
+        if gpu == 'all':
+            count = torch.cuda.device_count()
+            if count == 0:
+                raise RuntimeError("gpu='all' but no CUDA device is visible")
+            return list(range(count))
+        # the reference accepts gpu='mps' (core.py:147-148)
+        raise RuntimeError(f"gpu={gpu!r}: torbi_b200 is CUDA sm_100a only (no MPS / CPU dispatch)")
+    if gpu is None:
+        if observation is not None and observation.is_cuda:
+            return [observation.device.index]
+        raise RuntimeError(
+            'gpu=None selects the CPU path in torbi; torbi_b200 has no CPU fallback. '
+            'Pass gpu=<index> (or a list of indices, or "all").')
+    if isinstance(gpu, int):
+        return [gpu]
+    devices = [int(g) for g in gpu]
+    if not devices:
+        raise ValueError('gpu must name at least one device')
+    return devices
+
+
+def lpt_shards(costs: Sequence[int], shards: int) -> List[List[int]]:
+    """Longest-processing-time-first assignment of items to `shards` bins.
+    Returns per-bin item indices in ascending order (original order kept)."""
+    shards = max(1, min(shards, len(costs)))
+    order = sorted(range(len(costs)), key=lambda i: -int(costs[i]))
+    load = [0] * shards
+    bins: List[List[int]] = [[] for _ in range(shards)]
+    for item in order:
+        k = load.index(min(load))
+        bins[k].append(item)
+        load[k] += int(costs[item])
+    return [sorted(b) for b in bins]
+
+
+###############################################################################
+# Tensor API
+###############################################################################
+
+
+def _conversion_mode(conversion: Optional[str]) -> str:
+    mode = conversion or os.environ.get('TORBI_B200_CONVERSION', 'fused')
+    if mode not in ('fused', 'host', 'torch'):
+        raise ValueError(f"conversion must be 'fused', 'host' or 'torch', got {mode!r}")
+    return mode
+
+
+def _prepare_observation(observation, log_probs, device, mode):
+    """core.py:189-197.  Returns (fp32 tensor on `device`, kernel flags)."""
+    tiny = torch.finfo(torch.float32).tiny
+    if mode == 'fused':
+        flags = _ffi.EPS_FLOOR
+        if not log_probs:
+            if observation.dtype == torch.float32:
+                flags |= _ffi.OBS_IS_PROBABILITY
+            else:
+                # the reference takes the log in the INPUT dtype, then casts (core.py:190-191)
+                observation = torch.log(observation)
+        return observation.to(device=device, dtype=torch.float32), flags
+    if mode == 'host':
+        # exactly the reference's CPU ops, then one host->device copy
+        observation = observation.detach().to('cpu')
+        if not log_probs:
+            observation = torch.log(observation)
+        observation = observation.to(dtype=torch.float32, copy=True)
+    else:
+        # the reference's own CUDA route: same ops, run by torch on the device
+        if not log_probs:
+            observation = torch.log(observation)
+        observation = observation.to(device=device, dtype=torch.float32, copy=True)
+    torch.exp_(observation)
+    observation += tiny
+    torch.log_(observation)
+    return observation.to(device), 0
+
+
+def _from_probabilities_one(observation, batch_frames, transition, initial, log_probs,
+                            device, mode, return_posterior=False):
+    batch, frames, states = observation.shape
+    tiny = torch.finfo(torch.float32).tiny
+
+    # Default to uniform initial probabilities (core.py:161-172)
+    if initial is None:
+        initial = torch.full(
+            (states,), math.log((1. / states) + tiny), dtype=torch.float32, device=device)
+    else:
+        if not log_probs:
+            initial = torch.log(initial)
+        initial = initial.to(device=device, dtype=torch.float32)
+
+    # Default to uniform transition probabilities (core.py:175-186)
+    if transition is None:
+        transition = torch.full(
+            (states, states), math.log(1. / states), dtype=torch.float32, device=device)
+    else:
+        if not log_probs:
+            transition = torch.log(transition)
+        transition = transition.to(device=device, dtype=torch.float32)
+
+    observation, flags = _prepare_observation(observation, log_probs, device, mode)
+    return decode(observation, batch_frames, transition, initial, flags=flags,
+                  return_posterior=return_posterior)
+
+
+def from_probabilities(
+    observation: torch.Tensor,
+    batch_frames: Optional[torch.Tensor] = None,
+    transition: Optional[torch.Tensor] = None,
+    initial: Optional[torch.Tensor] = None,
+    log_probs: bool = False,
+    gpu: Gpu = None,
+    num_threads: Optional[int] = 1,
+    *,
+    conversion: Optional[str] = None,
+) -> torch.Tensor:
+    """Decode a time-varying categorical distribution
+
+    Arguments
+        observation
+            Time-varying categorical distribution
+            shape=(batch, frames, states)
+        batch_frames
+            Number of frames in each batch item; defaults to all
+            shape=(batch,)
+        transition
+            Categorical transition matrix; defaults to uniform
+            shape=(states, states), indexed [destination][source]
+        initial
+            Categorical initial distribution; defaults to uniform
+            shape=(states,)
+        log_probs
+            Whether inputs are in (natural) log space
+        gpu
+            GPU index to use for decoding; a sequence of indices or 'all' shards
+            the batch items across those GPUs. None uses the device of a CUDA
+            `observation` (there is no CPU path).
+        num_threads
+            Ignored (CPU threads in the reference)
+        conversion
+            'fused' (default): log / eps floor computed inside the kernel;
+            'host': the reference's exact CPU torch ops; 'torch': torch ops on
+            the GPU. Also settable through TORBI_B200_CONVERSION.
+
+    Returns
+        indices
+            The decoded bin indices, int32, on the (first) GPU
+            shape=(batch, frames)
+    """
+    del num_threads
+    batch, frames, states = observation.shape           # core.py:146 (ValueError if not 3-D)
+    devices = _resolve_devices(gpu, observation)
+    mode = _conversion_mode(conversion)
+
+    if batch_frames is None:                             # core.py:152-158
+        batch_frames = torch.full((batch,), frames, dtype=torch.int32)
+    host_frames = batch_frames.detach().to(device='cpu', dtype=torch.int32)
+
+    if len(devices) == 1 or batch == 1:
+        device = torch.device(f'cuda:{devices[0]}')
+        return _from_probabilities_one(
+            observation, host_frames, transition, initial, log_probs, device, mode)
+
+    # Several GPUs: independent items, longest first, one host thread per GPU;
+    # the only cross-device traffic is the gather of the int32 rows.
+    shards = lpt_shards(host_frames.tolist(), len(devices))
+    home = torch.device(f'cuda:{devices[0]}')
+    indices = torch.empty((batch, frames), dtype=torch.int32, device=home)
+    errors: List[BaseException] = []
+
+    def work(k, items):
+        try:
+            device = torch.device(f'cuda:{devices[k]}')
+            select = torch.tensor(items, dtype=torch.long)
+            part = observation.index_select(0, select.to(observation.device))
+            with torch.cuda.device(device):
+                rows = _from_probabilities_one(
+                    part, host_frames[select], transition, initial, log_probs, device, mode)
+                torch.cuda.current_stream(device).synchronize()
+            indices.index_copy_(0, select.to(home), rows.to(home))
+        except BaseException as error:  # noqa: BLE001 - re-raised on the caller's thread
+            errors.append(error)
+
+    threads = [threading.Thread(target=work, args=(k, items)) for k, items in enumerate(shards)]
+    for thread in threads:
+        thread.start()
+    for thread in threads:
+        thread.join()
+    if errors:
+        raise errors[0]
+    return indices
+
+
+def from_file(
+    input_file: Union[str, os.PathLike],
+    transition_file: Optional[Union[str, os.PathLike]] = None,
+    initial_file: Optional[Union[str, os.PathLike]] = None,
+    log_probs: bool = False,
+    gpu: Gpu = None,
+    num_threads: Optional[int] = 1
+) -> torch.Tensor:
+    """Decode a time-varying categorical distribution file
+
+    Arguments
+        input_file
+            Time-varying categorical distribution file
+            shape=(frames, states)
+        transition_file
+            Categorical transition matrix file; defaults to uniform
+            shape=(states, states)
+        initial_file
+            Categorical initial distribution file; defaults to uniform
+            shape=(states,)
+        log_probs
+            Whether inputs are in (natural) log space
+        gpu
+            GPU index to use for decoding
+        num_threads
+            Ignored
+
+    Returns
+        indices
+            The decoded bin indices
+            shape=(1, frames)   (as the reference actually returns, core.py:244,261)
+    """
+    # Load observations (core.py:244)
+    observation = torch.load(input_file, map_location='cpu').unsqueeze(dim=0)
+
+    # Load transition probabilities; logged WITHOUT tiny here (core.py:247-250)
+    if transition_file:
+        transition = torch.load(transition_file, map_location='cpu')
+        if log_probs:
+            transition = torch.log(transition)
+    else:
+        transition = None
+
+    # Load initial distribution, used raw (core.py:255-258)
+    initial = torch.load(initial_file, map_location='cpu') if initial_file else None
+
+    return from_probabilities(
+        observation=observation,
+        transition=transition,
+        initial=initial,
+        log_probs=log_probs,
+        gpu=gpu,
+        num_threads=num_threads)
+
+
+def from_file_to_file(
+    input_file: Union[str, os.PathLike],
+    output_file: Union[str, os.PathLike],
+    transition_file: Optional[Union[str, os.PathLike]] = None,
+    initial_file: Optional[Union[str, os.PathLike]] = None,
+    log_probs: bool = False,
+    gpu: Gpu = None,
+    num_threads: Optional[int] = None
+) -> None:
+    """Decode a time-varying categorical distribution file and save
+    (core.py:270-307; the saved tensor has shape (1, frames) like the reference's)"""
+    indices = from_file(
+        input_file, transition_file, initial_file, log_probs, gpu=gpu, num_threads=num_threads)
+    torch.save(indices, output_file)
+
+
+def from_files_to_files(
+    input_files: List[Union[str, os.PathLike]],
+    output_files: List[Union[str, os.PathLike]],
+    transition_file: Optional[Union[str, os.PathLike]] = None,
+    initial_file: Optional[Union[str, os.PathLike]] = None,
+    log_probs: bool = False,
+    gpu: Gpu = None,
+    num_threads: Optional[int] = None
+) -> None:
+    """Decode time-varying categorical distribution files and save
+
+    Arguments as /root/reference/torbi/core.py:310-339.  With several GPUs the
+    files are sharded across them by size (a proxy for frame count), longest
+    first; each GPU runs its own loader / decode / save loop.
+    """
+    # Load transition probabilities; logged WITH tiny here (core.py:341-347)
+    if transition_file:
+        transition = torch.load(transition_file, map_location='cpu')
+        if log_probs:
+            transition = torch.log(transition + torch.finfo(transition.dtype).tiny)
+    else:
+        transition = None
+
+    # Load initial distribution (core.py:350-353)
+    initial = torch.load(initial_file, map_location='cpu') if initial_file else None
+
+    # Preserve file mapping (core.py:356-358)
+    mapping = {
+        input_file: output_file
+        for input_file, output_file in zip(input_files, output_files)}
+
+    devices = _resolve_devices(gpu)
+    if len(devices) == 1:
+        from_dataloader(
+            dataloader=torbi_b200.data.loader(input_files),
+            output_files=mapping,
+            transition=transition,
+            initial=initial,
+            log_probs=log_probs,
+            gpu=devices[0],
+            num_threads=num_threads)
+        return
+
+    sizes = [os.path.getsize(file) for file in input_files]
+    shards = lpt_shards(sizes, len(devices))
+    errors: List[BaseException] = []
+
+    def work(k, items):
+        try:
+            from_dataloader(
+                dataloader=torbi_b200.data.loader([input_files[i] for i in items]),
+                output_files=mapping,
+                transition=transition,
+                initial=initial,
+                log_probs=log_probs,
+                gpu=devices[k],
+                num_threads=num_threads,
+                progress=(k == 0))
+        except BaseException as error:  # noqa: BLE001
+            errors.append(error)
+
+    threads = [threading.Thread(target=work, args=(k, items)) for k, items in enumerate(shards)]
+    for thread in threads:
+        thread.start()
+    for thread in threads:
+        thread.join()
+    if errors:
+        raise errors[0]
+
+
+###############################################################################
+# Utilities
+###############################################################################
+
+
+def from_dataloader(
+    dataloader: torch.utils.data.DataLoader,
+    output_files: Dict[
+        Union[str, bytes, os.PathLike],
+        Union[str, bytes, os.PathLike]],
+    transition: Optional[torch.Tensor] = None,
+    initial: Optional[torch.Tensor] = None,
+    log_probs: bool = False,
+    gpu: Gpu = None,
+    num_threads: Optional[int] = 1,
+    progress: bool = True
+) -> None:
+    """Decode time-varying categorical distributions from dataloader
+    (core.py:376-463): decode each collated batch, then save one int32
+    `(frames,)` tensor per input file."""
+    bar = _progress(len(dataloader.dataset)) if progress else None
+
+    for observation, batch_frames, batch_chunks, input_filenames in dataloader:
+
+        indices = from_probabilities(
+            observation=observation,
+            batch_frames=batch_frames,
+            transition=transition,
+            initial=initial,
+            log_probs=log_probs,
+            gpu=gpu,
+            num_threads=num_threads)
+
+        filenames = [output_files[file] for file in input_filenames]
+
+        if torbi_b200.MIN_CHUNK_SIZE is not None:
+            # Combine chunks (core.py:438-448)
+            separated = torbi_b200.data.separate(
+                indices=indices.cpu(), batch_chunks=batch_chunks, batch_frames=batch_frames)
+            for item, filename in zip(separated, filenames):
+                save(item.detach(), filename)
+        else:
+            # core.py:452-457
+            for item, filename, frames in zip(indices.cpu().detach(), filenames, batch_frames.cpu()):
+                save_masked(item, filename, frames)
+
+        if bar is not None:
+            bar.update(len(input_filenames))
+
+    if bar is not None:
+        bar.close()
+
+
+def _progress(total):
+    try:
+        import tqdm
+        return tqdm.tqdm(total=total, desc=torbi_b200.CONFIG, dynamic_ncols=True)
+    except ImportError:
+        return None
+
+
+def save(tensor, file):
+    """Save tensor (core.py:466-468)"""
+    torch.save(tensor.clone(), file)
+
+
+def save_masked(tensor, file, length):
+    """Save masked tensor (core.py:471-473)"""
+    torch.save(tensor[..., :length].clone(), file)

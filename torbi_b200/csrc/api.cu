@@ -1,0 +1,391 @@
+// C ABI of libtorbi_b200.so (declared in include/torbi_b200.h): validation,
+// workspace carving, kernel selection, and the host-buffer / multi-device
+// entries.  Replaces viterbi_decode_cuda and its launch glue
+// (/root/reference/torbi/csrc/cuda/viterbi.cu:203-362) -- but validates its
+// arguments, checks every launch, runs on the caller's stream and never
+// touches the current-device setting of the caller.
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+using namespace torbi_b200;
+
+namespace {
+
+thread_local char g_error[512] = "";
+thread_local const char *g_last_kernel = "none";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int fail_cuda(cudaError_t e, const char *what) {
+    return fail(TORBI_B200_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+struct DeviceInfo {
+    int sm_count = 0;
+    int cc_major = 0;
+    bool ok = false;
+};
+
+std::mutex g_dev_mutex;
+std::map<int, DeviceInfo> g_devices;
+
+// cudaGetDeviceProperties on every call is what the reference does
+// (viterbi.cu:217-218, :271-272); here it is cached per device.
+int device_info(int device, DeviceInfo *out) {
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    auto it = g_devices.find(device);
+    if (it == g_devices.end()) {
+        DeviceInfo d;
+        cudaError_t e = cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device);
+        if (e == cudaSuccess)
+            e = cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, device);
+        if (e != cudaSuccess) return fail_cuda(e, "query device");
+        d.ok = true;
+        it = g_devices.emplace(device, d).first;
+    }
+    *out = it->second;
+    if (out->cc_major != 10)
+        return fail(TORBI_B200_ERR_CUDA,
+                    "device %d has compute capability %d.x; libtorbi_b200 carries sm_100a code only",
+                    device, out->cc_major);
+    return TORBI_B200_OK;
+}
+
+int validate_shape(int64_t B, int64_t T, int64_t S) {
+    if (B < 1 || T < 1 || S < 1)
+        return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "batch, frames and states must be >= 1 (got %lld, %lld, %lld)",
+                    (long long)B, (long long)T, (long long)S);
+    if (S > 65535)
+        return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "states = %lld exceeds 65535 (uint16 backpointers)", (long long)S);
+    if (B > 0x7fffffff || T > 0x7fffffff)
+        return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "batch and frames must fit in int32");
+    return TORBI_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int torbi_b200_abi_version(void) { return TORBI_B200_ABI_VERSION; }
+
+const char *torbi_b200_last_error(void) { return g_error; }
+
+uint64_t torbi_b200_launch_count(void) { return g_launches.load(); }
+
+const char *torbi_b200_last_kernel(void) { return g_last_kernel; }
+
+int torbi_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int usable = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10)
+            ++usable;
+    }
+    return usable;
+}
+
+size_t torbi_b200_workspace_bytes(int64_t B, int64_t T, int64_t S, uint32_t) {
+    if (validate_shape(B, T, S) != TORBI_B200_OK) return 0;
+    return carve_workspace(nullptr, B, T, S).bytes;
+}
+
+int torbi_b200_decode(const float *observation, const int32_t *batch_frames,
+                      const float *transition, const float *initial, int64_t B, int64_t T,
+                      int64_t S, uint32_t flags, int32_t *indices, float *posterior,
+                      void *workspace, size_t workspace_bytes, void *stream_) {
+    g_error[0] = 0;
+    int rc = validate_shape(B, T, S);
+    if (rc) return rc;
+    if (!observation || !batch_frames || !transition || !initial || !indices || !workspace)
+        return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+    int64_t max_frames = 0;
+    for (int64_t b = 0; b < B; ++b) {
+        // the reference trusts these and reads out of bounds for 0 (viterbi.cpp:152)
+        if (batch_frames[b] < 1 || batch_frames[b] > T)
+            return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "batch_frames[%lld] = %d outside [1, %lld]",
+                        (long long)b, batch_frames[b], (long long)T);
+        max_frames = std::max<int64_t>(max_frames, batch_frames[b]);
+    }
+    if (reinterpret_cast<uintptr_t>(workspace) % 256)
+        return fail(TORBI_B200_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    Workspace ws = carve_workspace(workspace, B, T, S);
+    if (workspace_bytes < ws.bytes)
+        return fail(TORBI_B200_ERR_WORKSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, ws.bytes);
+
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
+    DeviceInfo info;
+    rc = device_info(device, &info);
+    if (rc) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+
+    // lengths and the longest-first processing order go to the device
+    std::vector<int32_t> order(pad_batch(B), -1);
+    std::iota(order.begin(), order.begin() + B, 0);
+    std::stable_sort(order.begin(), order.begin() + B,
+                     [&](int32_t x, int32_t y) { return batch_frames[x] > batch_frames[y]; });
+    e = cudaMemcpyAsync(ws.frames, batch_frames, sizeof(int32_t) * B, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(ws.order, order.data(), sizeof(int32_t) * order.size(),
+                            cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws.sync, 0, sizeof(uint32_t) * kSyncWords, stream);
+    if (e != cudaSuccess) return fail_cuda(e, "stage batch_frames");
+    // `order` is pageable host memory: the async copy has been staged by the
+    // time cudaMemcpyAsync returns, so the vector may go out of scope.
+
+    ForwardArgs a{};
+    a.observation = observation;
+    a.transition = transition;
+    a.initial = initial;
+    a.posterior = posterior;
+    a.B = B; a.T = T; a.S = S;
+    a.max_frames = max_frames;
+    a.flags = flags;
+    a.sm_count = info.sm_count;
+    a.ws = ws;
+
+    bool tiled = forward_tiled_supported(a) && !(flags & TORBI_B200_FORCE_GENERIC);
+    if ((flags & TORBI_B200_FORCE_TILED) && !tiled)
+        return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "tiled kernel does not support this shape");
+    if (tiled) {
+        e = launch_forward_tiled(a, stream);
+        g_last_kernel = "forward_tiled";
+    } else {
+        e = launch_forward_generic(a, stream);
+        g_last_kernel = "forward_generic";
+    }
+    if (e != cudaSuccess) return fail_cuda(e, g_last_kernel);
+    e = launch_backtrace(ws, indices, B, T, S, stream);
+    if (e != cudaSuccess) return fail_cuda(e, "backtrace");
+    g_launches += 2;
+    return TORBI_B200_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Host-buffer entries
+// ---------------------------------------------------------------------------
+namespace {
+
+struct Arena {
+    void *base = nullptr;
+    size_t bytes = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex busy;  // one decode at a time per device arena
+};
+
+std::mutex g_arena_mutex;
+std::map<int, Arena *> g_arenas;
+
+Arena *arena_for(int device) {
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    auto it = g_arenas.find(device);
+    if (it == g_arenas.end()) it = g_arenas.emplace(device, new Arena()).first;
+    return it->second;
+}
+
+struct DeviceGuard {
+    int previous = -1;
+    explicit DeviceGuard(int device) {
+        cudaGetDevice(&previous);
+        cudaSetDevice(device);
+    }
+    ~DeviceGuard() {
+        if (previous >= 0) cudaSetDevice(previous);
+    }
+};
+
+// Decode `count` items (given by index into the caller's batch) on one device.
+int decode_items_on_device(const float *observation, const int32_t *batch_frames,
+                           const float *transition, const float *initial,
+                           const int32_t *items, int64_t count, int64_t T, int64_t S,
+                           uint32_t flags, int32_t *indices, float *posterior, int device) {
+    DeviceGuard guard(device);
+    DeviceInfo info;
+    int rc = device_info(device, &info);
+    if (rc) return rc;
+    Arena *arena = arena_for(device);
+    std::lock_guard<std::mutex> lock(arena->busy);
+
+    const size_t obs_bytes = align_up(sizeof(float) * count * T * S, 256);
+    const size_t tr_bytes = align_up(sizeof(float) * S * S, 256);
+    const size_t init_bytes = align_up(sizeof(float) * S, 256);
+    const size_t idx_bytes = align_up(sizeof(int32_t) * count * T, 256);
+    const size_t post_bytes = posterior ? align_up(sizeof(float) * count * S, 256) : 0;
+    const size_t ws_bytes = carve_workspace(nullptr, count, T, S).bytes;
+    const size_t total = obs_bytes + tr_bytes + init_bytes + idx_bytes + post_bytes + ws_bytes;
+
+    cudaError_t e;
+    if (!arena->stream) {
+        e = cudaStreamCreateWithFlags(&arena->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaStreamCreate");
+    }
+    if (arena->bytes < total) {
+        if (arena->base) cudaFree(arena->base);
+        arena->base = nullptr;
+        arena->bytes = 0;
+        e = cudaMalloc(&arena->base, total);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(TORBI_B200_ERR_OUT_OF_MEMORY, "device %d: cannot allocate %zu bytes: %s",
+                        device, total, cudaGetErrorString(e));
+        }
+        arena->bytes = total;
+    }
+    char *p = static_cast<char *>(arena->base);
+    float *d_obs = reinterpret_cast<float *>(p); p += obs_bytes;
+    float *d_tr = reinterpret_cast<float *>(p); p += tr_bytes;
+    float *d_init = reinterpret_cast<float *>(p); p += init_bytes;
+    int32_t *d_idx = reinterpret_cast<int32_t *>(p); p += idx_bytes;
+    float *d_post = posterior ? reinterpret_cast<float *>(p) : nullptr; p += post_bytes;
+    void *d_ws = p;
+    cudaStream_t stream = arena->stream;
+
+    e = cudaMemcpyAsync(d_tr, transition, sizeof(float) * S * S, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_init, initial, sizeof(float) * S, cudaMemcpyHostToDevice, stream);
+    // items that are consecutive in the caller's batch travel in one copy
+    std::vector<int32_t> frames(count);
+    for (int64_t i = 0; i < count && e == cudaSuccess;) {
+        int64_t run = 1;
+        while (i + run < count && items[i + run] == items[i] + run) ++run;
+        e = cudaMemcpyAsync(d_obs + i * T * S, observation + (int64_t)items[i] * T * S,
+                            sizeof(float) * run * T * S, cudaMemcpyHostToDevice, stream);
+        i += run;
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "host->device copy");
+    for (int64_t i = 0; i < count; ++i) frames[i] = batch_frames[items[i]];
+
+    rc = torbi_b200_decode(d_obs, frames.data(), d_tr, d_init, count, T, S, flags, d_idx, d_post,
+                           d_ws, ws_bytes, stream);
+    if (rc) return rc;
+
+    for (int64_t i = 0; i < count && e == cudaSuccess;) {
+        int64_t run = 1;
+        while (i + run < count && items[i + run] == items[i] + run) ++run;
+        e = cudaMemcpyAsync(indices + (int64_t)items[i] * T, d_idx + i * T,
+                            sizeof(int32_t) * run * T, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess && posterior)
+            e = cudaMemcpyAsync(posterior + (int64_t)items[i] * S, d_post + i * S,
+                                sizeof(float) * run * S, cudaMemcpyDeviceToHost, stream);
+        i += run;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return fail_cuda(e, "device->host copy / synchronize");
+    return TORBI_B200_OK;
+}
+
+int validate_host_args(const float *observation, const int32_t *batch_frames,
+                       const float *transition, const float *initial, int64_t B, int64_t T,
+                       int64_t S, const int32_t *indices) {
+    int rc = validate_shape(B, T, S);
+    if (rc) return rc;
+    if (!observation || !batch_frames || !transition || !initial || !indices)
+        return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+    for (int64_t b = 0; b < B; ++b)
+        if (batch_frames[b] < 1 || batch_frames[b] > T)
+            return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "batch_frames[%lld] = %d outside [1, %lld]",
+                        (long long)b, batch_frames[b], (long long)T);
+    return TORBI_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int torbi_b200_decode_host(const float *observation, const int32_t *batch_frames,
+                           const float *transition, const float *initial, int64_t B, int64_t T,
+                           int64_t S, uint32_t flags, int32_t *indices, float *posterior,
+                           int device) {
+    g_error[0] = 0;
+    int rc = validate_host_args(observation, batch_frames, transition, initial, B, T, S, indices);
+    if (rc) return rc;
+    std::vector<int32_t> items(B);
+    std::iota(items.begin(), items.end(), 0);
+    return decode_items_on_device(observation, batch_frames, transition, initial, items.data(), B,
+                                  T, S, flags, indices, posterior, device);
+}
+
+int torbi_b200_decode_host_multi(const float *observation, const int32_t *batch_frames,
+                                 const float *transition, const float *initial, int64_t B,
+                                 int64_t T, int64_t S, uint32_t flags, int32_t *indices,
+                                 float *posterior, const int *devices, int n_devices) {
+    g_error[0] = 0;
+    int rc = validate_host_args(observation, batch_frames, transition, initial, B, T, S, indices);
+    if (rc) return rc;
+    if (!devices || n_devices < 1)
+        return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "need at least one device");
+    const int n = (int)std::min<int64_t>(n_devices, B);
+
+    // longest-processing-time-first: cost of an item is proportional to its
+    // frame count (S^2 cells per frame, same S for all items)
+    std::vector<int32_t> by_length(B);
+    std::iota(by_length.begin(), by_length.end(), 0);
+    std::stable_sort(by_length.begin(), by_length.end(),
+                     [&](int32_t x, int32_t y) { return batch_frames[x] > batch_frames[y]; });
+    std::vector<std::vector<int32_t>> shard(n);
+    std::vector<int64_t> load(n, 0);
+    for (int32_t item : by_length) {
+        int k = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        shard[k].push_back(item);
+        load[k] += batch_frames[item];
+    }
+    for (auto &s : shard) std::sort(s.begin(), s.end());  // contiguous runs copy together
+
+    std::vector<int> status(n, TORBI_B200_OK);
+    std::vector<std::string> message(n);
+    std::vector<std::thread> workers;
+    for (int k = 0; k < n; ++k) {
+        workers.emplace_back([&, k] {
+            status[k] = decode_items_on_device(observation, batch_frames, transition, initial,
+                                               shard[k].data(), (int64_t)shard[k].size(), T, S,
+                                               flags, indices, posterior, devices[k]);
+            if (status[k]) message[k] = torbi_b200_last_error();
+        });
+    }
+    for (auto &w : workers) w.join();
+    for (int k = 0; k < n; ++k)
+        if (status[k]) return fail(status[k], "device %d: %s", devices[k], message[k].c_str());
+    return TORBI_B200_OK;
+}
+
+void torbi_b200_release(void) {
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    for (auto &kv : g_arenas) {
+        Arena *a = kv.second;
+        std::lock_guard<std::mutex> busy(a->busy);
+        DeviceGuard guard(kv.first);
+        if (a->base) cudaFree(a->base);
+        if (a->stream) cudaStreamDestroy(a->stream);
+        a->base = nullptr;
+        a->bytes = 0;
+        a->stream = nullptr;
+    }
+}
+
+}  // extern "C"

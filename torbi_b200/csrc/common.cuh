@@ -1,0 +1,84 @@
+// Shared device/host helpers for the torbi_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cfloat>
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "../../include/torbi_b200.h"
+
+namespace torbi_b200 {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// ---------------------------------------------------------------------------
+// Fused log-space conversion of one observation element.
+// Restates /root/reference/torbi/core.py:189-197:
+//     if not log_probs: observation = torch.log(observation)
+//     torch.exp_(observation); observation += finfo(float32).tiny; torch.log_(observation)
+// with the CUDA math library's expf/logf (what torch's CUDA exp/log kernels
+// call), no fast-math, no flush-to-zero.
+// ---------------------------------------------------------------------------
+template <uint32_t kFlags>
+__device__ __forceinline__ float convert_observation(float x) {
+    if constexpr (kFlags & TORBI_B200_OBS_IS_PROBABILITY) x = logf(x);
+    if constexpr (kFlags & TORBI_B200_EPS_FLOOR) x = logf(expf(x) + FLT_MIN);
+    return x;
+}
+
+__device__ __forceinline__ float convert_observation_rt(float x, uint32_t flags) {
+    if (flags & TORBI_B200_OBS_IS_PROBABILITY) x = logf(x);
+    if (flags & TORBI_B200_EPS_FLOOR) x = logf(expf(x) + FLT_MIN);
+    return x;
+}
+
+// (value, index) ordering of the reference's strict-`>` ascending scan
+// (/root/reference/torbi/csrc/viterbi.cpp:94-101): larger value wins, equal
+// values keep the LOWER source index.
+__device__ __forceinline__ bool better(float v, int i, float best, int best_i) {
+    return v > best || (v == best && i < best_i);
+}
+
+// Workspace layout shared by api.cu and the kernels.  All offsets 256-B aligned.
+struct Workspace {
+    int32_t *frames;        // (B,)  device copy of batch_frames
+    int32_t *order;         // (B,)  items sorted by length, longest first
+    int32_t *final_state;   // (B,)  argmax of the final forward scores
+    uint32_t *sync;         // scheduling / barrier words (zeroed per call)
+    float *score[2];        // ping-pong forward scores, (B_pad, S_pad) each
+    float *transition_pad;  // (S_pad, S_pad) -inf padded copy when S % 32 != 0, else unused
+    uint16_t *backptr;      // (B, T, S) uint16 backpointers; row 0 unused
+    size_t bytes;
+};
+
+constexpr size_t kSyncWords = 4096;
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline int64_t pad_states(int64_t S) { return (S + 31) / 32 * 32; }
+inline int64_t pad_batch(int64_t B) { return (B + 127) / 128 * 128; }
+
+inline Workspace carve_workspace(void *base, int64_t B, int64_t T, int64_t S) {
+    Workspace w{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void *p = base ? static_cast<char *>(base) + off : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    const int64_t Sp = pad_states(S), Bp = pad_batch(B);
+    w.frames = static_cast<int32_t *>(take(sizeof(int32_t) * B));
+    w.order = static_cast<int32_t *>(take(sizeof(int32_t) * Bp));
+    w.final_state = static_cast<int32_t *>(take(sizeof(int32_t) * B));
+    w.sync = static_cast<uint32_t *>(take(sizeof(uint32_t) * kSyncWords));
+    w.score[0] = static_cast<float *>(take(sizeof(float) * Bp * Sp));
+    w.score[1] = static_cast<float *>(take(sizeof(float) * Bp * Sp));
+    w.transition_pad = static_cast<float *>(take(sizeof(float) * Sp * Sp));
+    w.backptr = static_cast<uint16_t *>(take(sizeof(uint16_t) * B * T * S));
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace torbi_b200

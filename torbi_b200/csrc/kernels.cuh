@@ -1,0 +1,31 @@
+// Launcher interface between api.cu and the kernel translation units.
+#pragma once
+
+#include "common.cuh"
+
+namespace torbi_b200 {
+
+struct ForwardArgs {
+    const float *observation;  // device (B,T,S)
+    const float *transition;   // device (S,S) [dest][src]
+    const float *initial;      // device (S,)
+    float *posterior;          // device (B,S) or nullptr
+    int64_t B, T, S;
+    int64_t max_frames;        // max(batch_frames)
+    uint32_t flags;
+    int sm_count;
+    Workspace ws;
+};
+
+// forward_generic.cu -- one CTA per sequence, any S
+cudaError_t launch_forward_generic(const ForwardArgs &a, cudaStream_t stream);
+
+// forward_tiled.cu -- batch-tiled max-plus "GEMM" per timestep, persistent grid
+bool forward_tiled_supported(const ForwardArgs &a);
+cudaError_t launch_forward_tiled(const ForwardArgs &a, cudaStream_t stream);
+
+// backtrace.cu -- ragged backtrace + tail fill (viterbi.cpp:140-160, :219-221)
+cudaError_t launch_backtrace(const Workspace &ws, int32_t *indices, int64_t B, int64_t T,
+                             int64_t S, cudaStream_t stream);
+
+}  // namespace torbi_b200
