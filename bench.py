@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the one hot path: timesteps decoded per second, 1440 states,
+batch 512, 2000 frames, triangular transition (BASELINE.json config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl graft|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic input.  For
+N > 1 the driver launches one process per GPU (torchrun); every rank decodes its
+own batch of 512 sequences (weak scaling: the path shards over independent
+sequences, no data-path collective) and rank 0 prints ONE JSON line.
+
+  value      whole-job timesteps/s with inputs resident in HBM, CUDA events, max over ranks
+  e2e        the same through the C ABI host entry (torbi_b200_decode_host): pinned host
+             buffers, H2D of the observations and D2H of the indices inside the timed region
+  roofline   the forward kernel against the FP32 max-plus issue roofline and,
+             secondarily, its algorithmic HBM bytes against the measured copy bandwidth
+  cpu_baseline  the reference's own CPU operator (oracle/_ref) on this box's host cores,
+             on a bounded sample of the same workload (rank 0, N = 1 only)
+
+`--impl reference` times the reference's CPU implementation of the path instead.
+"""
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / 'tests' / 'golden'))
+
+METRIC = 'timesteps decoded/sec, 1440 states batch 512'
+UNIT = 'timesteps/s'
+
+
+def parse_args():
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--gpus', type=int, default=1)
+    parser.add_argument('--steps', type=int, default=5)
+    parser.add_argument('--warmup', type=int, default=3)
+    parser.add_argument('--impl', default='graft', choices=['graft', 'reference'])
+    parser.add_argument('--batch', type=int, default=512)
+    parser.add_argument('--frames', type=int, default=2000)
+    parser.add_argument('--states', type=int, default=1440)
+    parser.add_argument('--no-e2e', action='store_true')
+    parser.add_argument('--no-cpu-baseline', action='store_true')
+    parser.add_argument('--kernel', default='auto', choices=['auto', 'generic', 'tiled'])
+    return parser.parse_args()
+
+
+def measured_peaks():
+    path = ROOT / 'MEASURED_PEAKS.json'
+    if path.exists():
+        peaks = json.loads(path.read_text())
+        return dict(hbm_gbs=float(peaks['hbm_gbs']), sm_max_mhz=float(peaks['sm_max_mhz']),
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source='fallback (B200_PROFILING.md)')
+
+
+def workload_config(args, world):
+    return {
+        'workload': 'BASELINE config 2: from_probabilities hot path, log-softmax(randn) observations, '
+                    'triangular pitch transition log(A+tiny), uniform initial, fused eps floor',
+        'states': args.states, 'batch_per_gpu': args.batch, 'frames': args.frames,
+        'global_batch': args.batch * world, 'sharding': f'independent sequences, {world} rank(s), no collective',
+        'l2_policy': 'inputs (5.9 GB/step) larger than L2; no flush needed',
+    }
+
+
+# ---------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------
+
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
+                 '-i', str(self.index), '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, sm_max, power, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); sm_max.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, value in zip(names, f[5:9]):
+                if value.lower() == 'active':
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(sm_max),
+                'power_w_max': max(power), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU reference (oracle/_ref = the unmodified reference operator)
+# ---------------------------------------------------------------------------
+
+def cpu_reference_runner():
+    """Returns (fn(obs, frames, A, init), kind, cores)."""
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    if oracle.ref_available():
+        def run(obs, frames, A, init):
+            return oracle.ref_decode(obs, frames, A, init, num_threads=cores)
+        return run, 'reference', cores
+
+    def run(obs, frames, A, init):
+        return oracle.c_decode(obs, frames, A, init, exact_scan=True, num_threads=cores)
+    return run, 'port', cores
+
+
+def cpu_sample(args, seconds, seed=1234):
+    """A bounded sample of the workload sized for about `seconds` of CPU work:
+    the first rows of the batch, truncated in time.  CPU throughput does not
+    depend on batch size (the reference loops over items sequentially,
+    viterbi.cpp:65)."""
+    import cases
+    run, kind, cores = cpu_reference_runner()
+    S = args.states
+    rng = np.random.default_rng(seed)
+    A = cases.log_triangular_transition(S)
+    init = np.full((S,), np.log(1.0 / S + np.finfo(np.float32).tiny), np.float32)
+    probe = cases.log_softmax(rng.standard_normal((1, 33, S)))
+    run(probe[:, :5], np.array([5], np.int32), A, init)                 # warm the thread pool
+    t0 = time.perf_counter()
+    run(probe, np.array([33], np.int32), A, init)
+    rate = 32 / (time.perf_counter() - t0)                              # recursion steps / s
+    total = int(max(64, min(rate * seconds, 8 * args.frames)))
+    B = max(1, min(8, total // args.frames)) if total >= args.frames else 1
+    T = max(2, min(args.frames, total // B))
+    obs = cases.log_softmax(rng.standard_normal((B, T, S)))
+    frames = np.full((B,), T, np.int32)
+
+    def step():
+        t0 = time.perf_counter()
+        run(obs, frames, A, init)
+        return time.perf_counter() - t0
+    return step, B * T, kind, cores, f'{B} sequences x {T} frames of the same synthetic workload (S={S})'
+
+
+def bench_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if rank != 0:
+        return
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    step, timesteps, kind, cores, sample = cpu_sample(args, min(20.0, budget))
+    for _ in range(args.warmup):
+        step()
+    elapsed = sum(step() for _ in range(args.steps))
+    value = timesteps * args.steps / elapsed
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * elapsed / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': workload_config(args, world),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+
+def make_workload(args, device, seed):
+    import cases
+    B, T, S = args.batch, args.frames, args.states
+    g = torch.Generator(device=device).manual_seed(seed)
+    obs = torch.empty((B, T, S), dtype=torch.float32, device=device)
+    chunk = max(1, B // 8)
+    for start in range(0, B, chunk):
+        x = torch.randn((min(chunk, B - start), T, S), device=device, generator=g)
+        obs[start:start + x.shape[0]] = torch.log_softmax(x, dim=-1)
+        del x
+    A = torch.from_numpy(cases.log_triangular_transition(S)).to(device)
+    init = torch.full((S,), float(np.log(1.0 / S + np.finfo(np.float32).tiny)),
+                      dtype=torch.float32, device=device)
+    frames = torch.full((B,), T, dtype=torch.int32)
+    return obs, frames, A, init
+
+
+def bench_graft(args):
+    import torch.distributed as dist
+    import torbi_b200
+    from torbi_b200 import _ffi
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; torbi_b200 has no CPU path '
+                         '(use --impl reference for the CPU reference)')
+    torch.cuda.set_device(local)
+    device = torch.device(f'cuda:{local}')
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib = _ffi.library()
+    B, T, S = args.batch, args.frames, args.states
+    obs, frames, A, init = make_workload(args, device, 1234 + rank)
+    flags = _ffi.EPS_FLOOR | _ffi.TIME_KERNELS
+    flags |= {'auto': 0, 'generic': _ffi.FORCE_GENERIC, 'tiled': _ffi.FORCE_TILED}[args.kernel]
+    timesteps_per_step = int(frames.sum())
+
+    fwd_ms, back_ms = [], []
+
+    def step(record):
+        indices = torbi_b200.decode(obs, frames, A, init, flags=flags)
+        if record:
+            import ctypes
+            f, b = ctypes.c_float(), ctypes.c_float()
+            _ffi.check(lib.torbi_b200_last_timing(ctypes.byref(f), ctypes.byref(b)))
+            fwd_ms.append(f.value); back_ms.append(b.value)
+        return indices
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    launches0 = lib.torbi_b200_launch_count()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        start.record()
+        for _ in range(args.steps):
+            indices = step(True)
+        end.record()
+        barrier()
+    elapsed_ms = start.elapsed_time(end)
+    launches = lib.torbi_b200_launch_count() - launches0
+    kernel = lib.torbi_b200_last_kernel().decode()
+    checksum = int(indices.sum(dtype=torch.int64))
+
+    # end to end through the C ABI host entry: pinned host buffers
+    e2e_ms = None
+    h2d = d2h = 0
+    if not args.no_e2e:
+        host_obs = torch.empty((B, T, S), dtype=torch.float32, pin_memory=True)
+        host_obs.copy_(obs)
+        host_A, host_init = A.cpu().pin_memory(), init.cpu().pin_memory()
+        host_out = torch.empty((B, T), dtype=torch.int32, pin_memory=True)
+        e2e_flags = flags & ~_ffi.TIME_KERNELS
+        h2d = host_obs.numel() * 4 + host_A.numel() * 4 + host_init.numel() * 4 + B * 4
+        d2h = host_out.numel() * 4
+        for _ in range(max(1, min(args.warmup, 2))):
+            torbi_b200.decode_host(host_obs, frames, host_A, host_init, gpu=local, flags=e2e_flags, out=host_out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            torbi_b200.decode_host(host_obs, frames, host_A, host_init, gpu=local, flags=e2e_flags, out=host_out)
+        barrier()
+        e2e_ms = 1e3 * (time.perf_counter() - t0)
+        assert int(host_out.sum(dtype=torch.int64)) == checksum, 'host entry disagrees with device entry'
+        del host_obs
+        lib.torbi_b200_release()
+
+    # max over ranks
+    times = torch.tensor([elapsed_ms, e2e_ms or 0.0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_max = float(times[0]), float(times[1])
+
+    if rank == 0:
+        peaks = measured_peaks()
+        total = timesteps_per_step * args.steps * world
+        value = total / (elapsed_ms * 1e-3)
+        sm_count = torch.cuda.get_device_properties(device).multi_processor_count
+        # FP32 max-plus issue roofline: 2*S^2 lane-ops per timestep,
+        # peak = SMs x 128 lanes x max SM clock
+        kernel_ms = statistics.mean(fwd_ms)
+        ops = 2.0 * S * S * timesteps_per_step
+        achieved = ops / (kernel_ms * 1e-3) / 1e12
+        peak = sm_count * 128 * peaks['sm_max_mhz'] * 1e6 / 1e12
+        hbm_bytes = (4.0 * S + 2.0 * S) * timesteps_per_step          # obs read + uint16 backpointers
+        hbm_achieved = hbm_bytes / (kernel_ms * 1e-3) / 1e9
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args, world),
+            'e2e': None if e2e_ms is None else {
+                'value': total / (e2e_max * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_max / args.steps,
+                'api': 'torbi_b200_decode_host (C ABI, pinned host buffers)'},
+            'gpu_launches': int(launches),
+            'clocks': clocks.summary(),
+            'roofline': {
+                'bound': 'fp32_alu_issue', 'kernel': kernel, 'achieved': achieved, 'peak': peak,
+                'unit': 'T lane-op/s', 'frac': achieved / peak, 'traffic': None,
+                'kernel_ms': kernel_ms, 'kernel_share_of_step': kernel_ms * args.steps / elapsed_ms,
+                'backtrace_ms': statistics.mean(back_ms),
+                'ops_per_launch': ops, 'peak_source': f"{sm_count} SMs x 128 lanes x {peaks['sm_max_mhz']} MHz, {peaks['source']}",
+                'timesteps_per_s_at_peak': peak * 1e12 / (2.0 * S * S),
+                'hbm': {'bound': 'hbm', 'achieved': hbm_achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                        'frac': hbm_achieved / peaks['hbm_gbs'], 'bytes_per_launch': hbm_bytes},
+            },
+            'checksum': checksum,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            step_cpu, timesteps, kind, cores, sample = cpu_sample(args, 15.0)
+            seconds = step_cpu()
+            line['cpu_baseline'] = {'value': timesteps / seconds, 'unit': UNIT, 'cores': cores,
+                                    'kind': kind, 'sample': sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        bench_reference(args)
+    else:
+        bench_graft(args)
+
+
+if __name__ == '__main__':
+    main()

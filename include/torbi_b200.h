@@ -55,6 +55,9 @@ extern "C" {
 /* kernel selection, for tests and profiling; default 0 lets the library pick */
 #define TORBI_B200_FORCE_GENERIC (1u << 8)      /* one CTA per sequence, any S                 */
 #define TORBI_B200_FORCE_TILED (1u << 9)        /* batch-tiled max-plus kernel                 */
+/* record CUDA events around the forward and backtrace kernels on the caller's
+ * stream so torbi_b200_last_timing can report their device time */
+#define TORBI_B200_TIME_KERNELS (1u << 10)
 
 TORBI_B200_API int torbi_b200_abi_version(void);
 
@@ -131,6 +134,12 @@ TORBI_B200_API void torbi_b200_release(void);
  * name of the forward kernel the last decode on this thread used. */
 TORBI_B200_API uint64_t torbi_b200_launch_count(void);
 TORBI_B200_API const char *torbi_b200_last_kernel(void);
+
+/* Device time of the forward and the backtrace kernel of the last
+ * torbi_b200_decode on this thread that was called with
+ * TORBI_B200_TIME_KERNELS.  Waits for those kernels to finish.  Either pointer
+ * may be NULL. */
+TORBI_B200_API int torbi_b200_last_timing(float *forward_ms, float *backtrace_ms);
 
 #ifdef __cplusplus
 }

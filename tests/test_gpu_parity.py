@@ -1,0 +1,366 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the oracle and with the
+golden vectors of the unmodified reference.  Integer outputs and fp32 forward
+scores are compared BIT-EXACT; nothing here reads /root/reference."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import torbi_b200
+from torbi_b200 import _ffi
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = {'auto': 0, 'generic': _ffi.FORCE_GENERIC}
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.int32)
+
+
+def cuda(x):
+    return torch.as_tensor(np.asarray(x)).to('cuda:0')
+
+
+def gpu_decode(obs, frames, A, init, flags=0):
+    indices, posterior = torbi_b200.decode(
+        cuda(obs), torch.as_tensor(np.asarray(frames)), cuda(A), cuda(init), flags=flags,
+        return_posterior=True)
+    torch.cuda.synchronize()
+    return indices.cpu().numpy(), posterior.cpu().numpy()
+
+
+def test_library_is_loaded_and_device_is_sm100():
+    assert torbi_b200.LIBRARY.exists()
+    assert _ffi.library().torbi_b200_device_count() >= 1
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+# ---------------------------------------------------------------------------
+# golden vectors of the reference (tests/golden/golden.npz)
+# ---------------------------------------------------------------------------
+
+@pytest.mark.parametrize('kernel', list(KERNELS))
+@pytest.mark.parametrize('name', list(cases.CASES))
+def test_decode_matches_reference_golden(name, kernel, golden, oracle):
+    """Gate (A): identical converted fp32 inputs -> bit-exact indices and scores."""
+    case = cases.CASES[name]()
+    obs, frames, A, init = oracle.ref_prepare(
+        case['observation'], case['batch_frames'], case['transition'], case['initial'],
+        case['log_probs'])
+    indices, posterior = gpu_decode(obs.numpy(), frames.numpy(), A.numpy(), init.numpy(),
+                                    flags=KERNELS[kernel])
+    assert np.array_equal(indices, golden[f'{name}/indices'])
+    assert np.array_equal(bits(posterior), bits(golden[f'{name}/posterior']))
+
+
+@pytest.mark.parametrize('conversion', ['host', 'fused', 'torch'])
+@pytest.mark.parametrize('name', list(cases.CASES))
+def test_from_probabilities_matches_reference_golden(name, conversion, golden):
+    """The public entry point against the reference's own from_probabilities
+    output (CPU path).  'host' repeats the reference's CPU conversion exactly;
+    'fused' converts inside the kernel (expf/logf of the CUDA math library)."""
+    case = cases.CASES[name]()
+
+    def tensor(x):
+        return None if x is None else torch.from_numpy(np.array(x))
+
+    observation = tensor(case['observation'])
+    before = observation.clone()
+    indices = torbi_b200.from_probabilities(
+        observation, tensor(case['batch_frames']), tensor(case['transition']),
+        tensor(case['initial']), log_probs=case['log_probs'], gpu=0, conversion=conversion)
+    assert indices.dtype == torch.int32 and indices.device.type == 'cuda'
+    assert torch.equal(observation, before)                     # caller's tensor untouched
+    assert np.array_equal(indices.cpu().numpy(), golden[f'{name}/api_indices'])
+
+
+def test_known_answer_on_gpu_like_reference_test_cuda():
+    # /root/reference/tests/test_core.py:27-46
+    case = cases.kat()
+    bins = torbi_b200.from_probabilities(
+        observation=torch.tensor(case['observation']).to('cuda:0'),
+        transition=torch.tensor(case['transition']).to('cuda:0'),
+        initial=torch.tensor(case['initial']).to('cuda:0'),
+        log_probs=False, gpu=0)
+    assert (bins == torch.tensor([1, 2, 2]).to('cuda:0')).all()
+    # gpu=None with CUDA inputs uses their device
+    bins = torbi_b200.from_probabilities(
+        observation=torch.tensor(case['observation']).to('cuda:0'),
+        transition=torch.tensor(case['transition']), initial=torch.tensor(case['initial']))
+    assert bins.tolist() == [[1, 2, 2]]
+
+
+# ---------------------------------------------------------------------------
+# seeded random inputs against the C oracle
+# ---------------------------------------------------------------------------
+
+def random_problem(seed, B, T, S, ragged=True, quant=None, transition='dense'):
+    rng = np.random.default_rng(seed)
+    obs = cases.log_softmax(rng.standard_normal((B, T, S)))
+    if transition == 'dense':
+        A = cases.log_softmax(rng.standard_normal((S, S)))
+    else:
+        A = cases.log_triangular_transition(S, min(87.208, S / 4))
+    init = cases.log_softmax(rng.standard_normal((S,)))
+    if quant:
+        obs = (np.round(obs * quant) / quant).astype(np.float32)
+        A = (np.round(A * quant) / quant).astype(np.float32)
+    frames = rng.integers(1, T + 1, size=B).astype(np.int32) if ragged else np.full(B, T, np.int32)
+    frames[0] = T
+    return obs, frames, A, init
+
+
+SHAPES = [
+    # (B, T, S, quant, transition)
+    (1, 50, 1440, None, 'dense'),
+    (8, 64, 1440, None, 'triangular'),
+    (37, 20, 1440, 1, 'dense'),
+    (130, 9, 1440, None, 'triangular'),
+    (3, 40, 1000, None, 'dense'),
+    (5, 33, 1441, 2, 'dense'),
+    (4, 16, 4096, None, 'dense'),
+    (70, 12, 96, 2, 'dense'),
+    (600, 6, 160, None, 'dense'),
+    (2, 300, 64, None, 'dense'),
+]
+
+
+@pytest.mark.parametrize('kernel', list(KERNELS))
+@pytest.mark.parametrize('shape', SHAPES, ids=[f'B{s[0]}-T{s[1]}-S{s[2]}' for s in SHAPES])
+def test_decode_matches_oracle(shape, kernel, oracle):
+    B, T, S, quant, transition = shape
+    obs, frames, A, init = random_problem(B * 1000 + S, B, T, S, quant=quant, transition=transition)
+    want_idx, want_post = oracle.c_decode(obs, frames, A, init, exact_scan=False, want_posterior=True)
+    indices, posterior = gpu_decode(obs, frames, A, init, flags=KERNELS[kernel])
+    assert np.array_equal(indices, want_idx)
+    assert np.array_equal(bits(posterior), bits(want_post))
+
+
+def test_padding_is_never_read(oracle):
+    # garbage (NaN) beyond batch_frames must not influence anything
+    obs, frames, A, init = random_problem(7, 6, 30, 200)
+    dirty = obs.copy()
+    for b, f in enumerate(frames):
+        dirty[b, f:] = np.nan
+    a, pa = gpu_decode(obs, frames, A, init)
+    b, pb = gpu_decode(dirty, frames, A, init)
+    assert np.array_equal(a, b) and np.array_equal(bits(pa), bits(pb))
+    assert np.array_equal(a, oracle.c_decode(obs, frames, A, init))
+
+
+def test_each_item_equals_decoding_it_alone():
+    obs, frames, A, init = random_problem(11, 9, 25, 1440, quant=1)
+    together, _ = gpu_decode(obs, frames, A, init)
+    for b in range(obs.shape[0]):
+        alone, _ = gpu_decode(obs[b:b + 1, :frames[b]], frames[b:b + 1], A, init)
+        assert np.array_equal(together[b, :frames[b]], alone[0])
+        assert (together[b, frames[b] - 1:] == alone[0, -1]).all()
+
+
+def test_fused_conversion_equals_torch_cuda_conversion():
+    """Contract (B) of SURVEY H6: expf/+tiny/logf inside the kernel == torch's
+    CUDA exp_/+=/log_ followed by a plain decode, bit for bit."""
+    rng = np.random.default_rng(3)
+    S = 256
+    prob = np.exp(cases.log_softmax(rng.standard_normal((4, 40, S)) * 12.0).astype(np.float64)).astype(np.float32)
+    A = cuda(cases.log_softmax(rng.standard_normal((S, S))))
+    init = cuda(cases.log_softmax(rng.standard_normal((S,))))
+    frames = torch.tensor([40, 7, 40, 1])
+    x = cuda(prob)
+    converted = torch.log(x)
+    torch.exp_(converted)
+    converted += torch.finfo(torch.float32).tiny
+    torch.log_(converted)
+    want, want_post = torbi_b200.decode(converted, frames, A, init, return_posterior=True)
+    got, got_post = torbi_b200.decode(
+        x, frames, A, init, flags=_ffi.OBS_IS_PROBABILITY | _ffi.EPS_FLOOR, return_posterior=True)
+    assert torch.equal(want, got)
+    assert torch.equal(want_post.view(torch.int32), got_post.view(torch.int32))
+
+
+def test_host_entry_matches_device_entry(oracle):
+    obs, frames, A, init = random_problem(21, 12, 30, 320)
+    want = oracle.c_decode(obs, frames, A, init)
+    host = torbi_b200.decode_host(
+        torch.from_numpy(obs).pin_memory(), torch.from_numpy(frames), torch.from_numpy(A),
+        torch.from_numpy(init), gpu=0)
+    assert host.device.type == 'cpu' and np.array_equal(host.numpy(), want)
+    devices = list(range(min(torch.cuda.device_count(), 8)))
+    multi, post = torbi_b200.decode_host(
+        torch.from_numpy(obs), torch.from_numpy(frames), torch.from_numpy(A),
+        torch.from_numpy(init), gpu=devices + [devices[0]], return_posterior=True)
+    assert np.array_equal(multi.numpy(), want)
+    _, want_post = oracle.c_decode(obs, frames, A, init, want_posterior=True)
+    assert np.array_equal(bits(post.numpy()), bits(want_post))
+
+
+def test_multi_gpu_list_api(oracle):
+    obs, frames, A, init = random_problem(22, 10, 20, 128)
+    want = oracle.c_decode(obs, frames, A, init)
+    devices = list(range(torch.cuda.device_count())) * 2        # >= 2 shards even on one GPU
+    got = torbi_b200.from_probabilities(
+        torch.from_numpy(obs), torch.from_numpy(frames), torch.from_numpy(A),
+        torch.from_numpy(init), log_probs=True, gpu=devices[:4], conversion='host')
+    assert got.device == torch.device('cuda:0')
+    # log(exp(x)+tiny) is the identity on these inputs, so the plain oracle applies
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_errors_on_gpu():
+    obs = torch.rand(2, 4, 5, device='cuda:0')
+    A, init = torch.rand(5, 5, device='cuda:0'), torch.rand(5, device='cuda:0')
+    with pytest.raises(ValueError, match='batch_frames'):
+        torbi_b200.decode(obs, torch.tensor([4, 0]), A, init)
+    with pytest.raises(ValueError, match='batch_frames'):
+        torbi_b200.decode(obs, torch.tensor([4, 5]), A, init)
+    with pytest.raises(RuntimeError, match='same device'):
+        torbi_b200.decode(obs, torch.tensor([4, 4]), A.cpu(), init)
+    # a good call still works afterwards
+    assert torbi_b200.decode(obs, torch.tensor([4, 4]), A, init).shape == (2, 4)
+
+
+# ---------------------------------------------------------------------------
+# full-size configs: size-independent properties + spot checks against the oracle
+# ---------------------------------------------------------------------------
+
+def replay_path_score(obs, A, init, path):
+    """fp32 score of `path` accumulated in the recursion's own order:
+    P = obs[0,i0] + init[i0];  P = obs[t,it] + (P + A[it, it-1])."""
+    p = np.float32(obs[0, path[0]]) + np.float32(init[path[0]])
+    for t in range(1, len(path)):
+        p = np.float32(obs[t, path[t]]) + np.float32(p + np.float32(A[path[t], path[t - 1]]))
+    return np.float32(p)
+
+
+def torch_convert(x):
+    """log(exp(x) + tiny) with torch's CUDA kernels (bit-identical to the fused
+    conversion, see test_fused_conversion_equals_torch_cuda_conversion)."""
+    y = x.clone()
+    torch.exp_(y)
+    y += torch.finfo(torch.float32).tiny
+    torch.log_(y)
+    return y
+
+
+def full_size_problem(B, T, S, seed=1234):
+    g = torch.Generator(device='cuda:0').manual_seed(seed)
+    obs = torch.log_softmax(torch.randn(B, T, S, device='cuda:0', generator=g), dim=-1)
+    A = cuda(cases.log_triangular_transition(S))
+    init = torch.full((S,), float(np.log(1.0 / S + np.finfo(np.float32).tiny)), device='cuda:0')
+    return obs, A, init
+
+
+def test_config2_full_size_properties(oracle):
+    """BASELINE config 2: S=1440, B=512, T=2000, triangular transition."""
+    B, T, S = 512, 2000, 1440
+    obs, A, init = full_size_problem(B, T, S)
+    frames = torch.full((B,), T, dtype=torch.int32)
+    indices, posterior = torbi_b200.decode(obs, frames, A, init, flags=_ffi.EPS_FLOOR,
+                                           return_posterior=True)
+    again = torbi_b200.decode(obs, frames, A, init, flags=_ffi.EPS_FLOOR)
+    assert torch.equal(indices, again)                           # deterministic
+    assert int(indices.min()) >= 0 and int(indices.max()) < S
+    # the final state is the first-occurrence argmax of the final scores
+    assert torch.equal(indices[:, -1].long(), posterior.argmax(dim=1))
+    # replaying each decoded path in fp32 reproduces the winning score exactly
+    A_host, init_host = A.cpu().numpy(), init.cpu().numpy()
+    for b in (0, 17, 255, 511):
+        path = indices[b].cpu().numpy()
+        score = replay_path_score(torch_convert(obs[b]).cpu().numpy(), A_host, init_host, path)
+        assert bits(score) == bits(posterior[b].max().cpu().numpy())
+    # spot check against the oracle: two whole items
+    for b in (3, 400):
+        want, want_post = oracle.c_decode(
+            torch_convert(obs[b:b + 1]).cpu().numpy(), [T], A_host, init_host, exact_scan=False,
+            want_posterior=True)
+        assert np.array_equal(indices[b].cpu().numpy(), want[0])
+        assert np.array_equal(bits(posterior[b].cpu().numpy()), bits(want_post[0]))
+
+
+def test_config3_ragged_batch(oracle):
+    """BASELINE config 3 (scaled to fit the test budget): S=1440, ragged lengths
+    log-uniform in [200, 6000], batch 48; checked per item (the reference cannot
+    index the padded batch, B*T*S >= 2^31 at full size)."""
+    B, S = 48, 1440
+    rng = np.random.default_rng(1234)
+    frames = np.exp(rng.uniform(np.log(200), np.log(6000), size=B)).round().astype(np.int32)
+    frames[0], frames[1] = 6000, 200
+    T = int(frames.max())
+    obs, A, init = full_size_problem(B, T, S, seed=4321)
+    indices, posterior = torbi_b200.decode(obs, torch.from_numpy(frames), A, init,
+                                           return_posterior=True)
+    idx = indices.cpu().numpy()
+    A_host, init_host = A.cpu().numpy(), init.cpu().numpy()
+    for b in range(B):
+        assert (idx[b, frames[b] - 1:] == idx[b, frames[b] - 1]).all()       # tail fill
+    for b in (0, 1, 7, 30):
+        f = int(frames[b])
+        score = replay_path_score(obs[b, :f].cpu().numpy(), A_host, init_host, idx[b, :f])
+        assert bits(score) == bits(posterior[b].max().cpu().numpy())
+    for b in (1, 5):
+        f = int(frames[b])
+        want = oracle.c_decode(obs[b:b + 1, :f].cpu().numpy(), [f], A_host, init_host, exact_scan=False)
+        assert np.array_equal(idx[b, :f], want[0])
+
+
+# ---------------------------------------------------------------------------
+# file drivers
+# ---------------------------------------------------------------------------
+
+def test_file_drivers(tmp_path, oracle):
+    rng = np.random.default_rng(8)
+    S = 96
+    lengths = [30, 5, 17, 1, 30, 12]
+    files = []
+    for i, f in enumerate(lengths):
+        x = torch.from_numpy(cases.log_softmax(rng.standard_normal((f, S))))
+        path = tmp_path / f'in{i}.pt'
+        torch.save(x, path)
+        files.append(path)
+    transition = torch.from_numpy(cases.triangular_transition(S, 9.5))       # probabilities
+    torch.save(transition, tmp_path / 'transition.pt')
+    initial = torch.from_numpy(cases.log_softmax(rng.standard_normal((S,))))  # log space
+    torch.save(initial, tmp_path / 'initial.pt')
+    outputs = [tmp_path / f'out{i}.pt' for i in range(len(files))]
+
+    old = torbi_b200.BATCH_SIZE
+    torbi_b200.BATCH_SIZE = 4                        # two batches
+    try:
+        torbi_b200.from_files_to_files(
+            files, outputs, tmp_path / 'transition.pt', tmp_path / 'initial.pt',
+            log_probs=True, gpu=0)
+    finally:
+        torbi_b200.BATCH_SIZE = old
+    tiny = torch.finfo(torch.float32).tiny
+    A = torch.log(transition + tiny).numpy()                                  # core.py:343-345
+    for path, out, f in zip(files, outputs, lengths):
+        got = torch.load(out)
+        assert got.dtype == torch.int32 and got.shape == (f,)
+        x = torch.load(path).unsqueeze(0)
+        want = oracle.ref_from_probabilities(x, None, torch.from_numpy(A), initial, True)
+        assert np.array_equal(got.numpy(), want[0])
+
+    # from_file: transition logged WITHOUT tiny (core.py:247-250), shape (1, frames)
+    got = torbi_b200.from_file(files[0], tmp_path / 'transition.pt', tmp_path / 'initial.pt',
+                               log_probs=True, gpu=0)
+    assert got.shape == (1, lengths[0])
+    want = oracle.ref_from_probabilities(
+        torch.load(files[0]).unsqueeze(0), None, torch.log(transition), initial, True)
+    assert np.array_equal(got.cpu().numpy(), want)
+    torbi_b200.from_file_to_file(files[2], tmp_path / 'single.pt', gpu=0, log_probs=True)
+    assert torch.load(tmp_path / 'single.pt').shape == (1, lengths[2])
+
+    # chunked mode: pieces decode independently and are re-joined per file
+    torbi_b200.MIN_CHUNK_SIZE = 4
+    try:
+        torbi_b200.from_files_to_files(files[:3], outputs[:3], log_probs=True, gpu=0)
+        for path, out, f in zip(files[:3], outputs[:3], lengths[:3]):
+            x = torch.load(path)
+            pieces = torbi_b200.chunk(x)
+            want = np.concatenate([
+                oracle.ref_from_probabilities(p.unsqueeze(0), None, None, None, True)[0]
+                for p in pieces])
+            assert np.array_equal(torch.load(out).numpy(), want)
+    finally:
+        torbi_b200.MIN_CHUNK_SIZE = None

@@ -1,0 +1,162 @@
+"""CPU: host-side logic of the drop-in (no GPU compute): library loading and
+exported symbols, argument validation, sharding, collate / separate, chunking,
+CLI parsing, configuration."""
+import ctypes
+import pathlib
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import torbi_b200
+from torbi_b200 import _ffi
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / 'include' / 'torbi_b200.h').read_text()
+    declared = re.findall(r'TORBI_B200_API\s+[\w\s\*]+?(torbi_b200_\w+)\s*\(', header)
+    assert len(declared) >= 11
+    lib = ctypes.CDLL(str(torbi_b200.LIBRARY))
+    for name in declared:
+        assert hasattr(lib, name), name
+    # and the Python binding covers all of them
+    assert set(declared) == set(_ffi.SIGNATURES)
+    assert _ffi.library().torbi_b200_abi_version() == _ffi.ABI_VERSION
+
+
+def test_flag_values_match_header():
+    header = (ROOT / 'include' / 'torbi_b200.h').read_text()
+    for name in ('OBS_IS_PROBABILITY', 'EPS_FLOOR', 'FORCE_GENERIC', 'FORCE_TILED', 'TIME_KERNELS'):
+        shift = int(re.search(rf'#define TORBI_B200_{name} \(1u << (\d+)\)', header).group(1))
+        assert getattr(_ffi, name) == 1 << shift
+    for name in ('INVALID_ARGUMENT', 'WORKSPACE', 'CUDA', 'OUT_OF_MEMORY'):
+        code = int(re.search(rf'#define TORBI_B200_ERR_{name} \((-\d+)\)', header).group(1))
+        assert getattr(_ffi, f'ERR_{name}') == code
+
+
+def test_workspace_bytes_and_shape_validation():
+    lib = _ffi.library()
+    # uint16 backpointers dominate: B*T*S*2
+    assert lib.torbi_b200_workspace_bytes(512, 2000, 1440, 0) >= 512 * 2000 * 1440 * 2
+    assert lib.torbi_b200_workspace_bytes(512, 2000, 1440, 0) < 512 * 2000 * 1440 * 2 * 1.02
+    assert lib.torbi_b200_workspace_bytes(0, 10, 10, 0) == 0
+    assert lib.torbi_b200_workspace_bytes(1, 10, 65536, 0) == 0
+    assert 'exceeds 65535' in _ffi.last_error()
+
+
+def test_no_cpu_fallback():
+    observation = torch.rand(1, 3, 3)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        torbi_b200.from_probabilities(observation)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        torbi_b200.decode(observation, torch.tensor([3]), torch.rand(3, 3), torch.rand(3))
+    with pytest.raises(RuntimeError, match='MPS'):
+        torbi_b200.from_probabilities(observation, gpu='mps')
+    with pytest.raises(ValueError):
+        torbi_b200.from_probabilities(torch.rand(3, 3), gpu=0)      # 2-D, like the reference
+
+
+def test_decode_validates_before_touching_the_gpu():
+    obs = torch.rand(2, 4, 5)
+    with pytest.raises(ValueError, match='transition'):
+        torbi_b200.decode(obs, torch.tensor([4, 4]), torch.rand(4, 5), torch.rand(5))
+    with pytest.raises(ValueError, match='float32'):
+        torbi_b200.decode(obs.double(), torch.tensor([4, 4]), torch.rand(5, 5), torch.rand(5))
+    # host entry: frames outside [1, T] rejected by the C side before any CUDA call
+    with pytest.raises(ValueError, match='batch_frames'):
+        torbi_b200.decode_host(obs, torch.tensor([4, 0]), torch.rand(5, 5), torch.rand(5), gpu=0)
+    with pytest.raises(ValueError, match='batch_frames'):
+        torbi_b200.decode_host(obs, torch.tensor([5, 1]), torch.rand(5, 5), torch.rand(5), gpu=[0, 1])
+
+
+def test_lpt_shards():
+    costs = [5, 100, 7, 90, 30, 30, 1, 60]
+    shards = torbi_b200.lpt_shards(costs, 3)
+    assert sorted(sum(shards, [])) == list(range(len(costs)))
+    loads = [sum(costs[i] for i in s) for s in shards]
+    assert max(loads) <= 1.25 * sum(costs) / 3
+    assert all(s == sorted(s) for s in shards)
+    assert torbi_b200.lpt_shards([3, 1], 8) == [[0], [1]]
+
+
+def test_collate_and_separate():
+    a = torch.arange(12, dtype=torch.float32).reshape(4, 3)
+    b = torch.arange(6, dtype=torch.float32).reshape(2, 3) + 100
+    observation, frames, chunks, files = torbi_b200.data.collate([(a, 'a.pt'), (b, 'b.pt')])
+    assert observation.shape == (2, 4, 3) and frames.tolist() == [4, 2] and chunks == [1, 1]
+    assert files == ('a.pt', 'b.pt')
+    assert torch.equal(observation[1, :2], b) and (observation[1, 2:] == 0).all()
+    # chunked files: one batch item per chunk, re-joined by separate()
+    observation, frames, chunks, _ = torbi_b200.data.collate(
+        [([a[:1], a[1:]], 'a.pt'), ([b], 'b.pt')])
+    assert observation.shape == (3, 3, 3) and frames.tolist() == [1, 3, 2] and chunks == [2, 1]
+    indices = torch.tensor([[7, 0, 0], [1, 2, 3], [4, 5, 0]])
+    joined = torbi_b200.data.separate(indices, chunks, frames)
+    assert [j.tolist() for j in joined] == [[7, 1, 2, 3], [4, 5]]
+    with pytest.raises(ValueError):
+        torbi_b200.data.collate([])
+
+
+def reference_split(observation, min_chunk_size, entropy_threshold):
+    """/root/reference/torbi/chunk.py:57-78 spelled out as a plain loop."""
+    x = observation.T
+    ent = -((torch.exp(x) * x).sum(dim=0) / torch.log(torch.tensor(x.shape[0])))
+    cand = ent < entropy_threshold
+    points, i = [], min_chunk_size
+    while i < x.shape[-1]:
+        if cand[i] and cand[i - 1]:
+            points.append(i)
+            i += min_chunk_size
+        else:
+            i += 1
+    return points
+
+
+def test_chunk_matches_reference_rule():
+    g = torch.Generator().manual_seed(1234)
+    frames, states = 400, 24
+    logits = torch.randn(frames, states, generator=g)
+    peaky = torch.rand(frames, generator=g) < 0.4
+    logits[peaky] *= 12.0
+    observation = torch.log_softmax(logits, dim=-1)
+    for min_chunk, threshold in [(8, 0.5), (25, 0.5), (3, 0.2), (500, 0.5)]:
+        expected = reference_split(observation, min_chunk, threshold)
+        assert torbi_b200.chunk.__module__  # module import sanity
+        from torbi_b200.chunk import split
+        assert split(observation, min_chunk, threshold) == expected
+        chunks = torbi_b200.chunk(observation, min_chunk, threshold)
+        assert len(chunks) == len(expected) + 1
+        assert torch.equal(torch.cat(chunks), observation)
+        assert all(c.shape[0] >= min(min_chunk, frames) for c in chunks[:-1])
+
+
+def test_cli_and_configure(tmp_path):
+    from torbi_b200.__main__ import parse_args
+    args = parse_args(['--input_files', 'a.pt', 'b.pt', '--output_files', 'c.pt', 'd.pt',
+                       '--log_probs', '--gpu', '0', '--unknown_flag', '1'])
+    assert args['gpu'] == 0 and args['log_probs'] and len(args['input_files']) == 2
+    assert set(args) == {'input_files', 'output_files', 'transition_file', 'initial_file',
+                         'log_probs', 'gpu', 'num_threads'}
+    args = parse_args(['--input_files', 'a.pt', '--output_files', 'c.pt', '--gpu', '0', '1'])
+    assert args['gpu'] == [0, 1]
+    config = tmp_path / 'config.py'
+    config.write_text('BATCH_SIZE = 64\nMIN_CHUNK_SIZE = 32\nNOT_A_CONSTANT = 1\n')
+    try:
+        torbi_b200.configure(config)
+        assert torbi_b200.BATCH_SIZE == 64 and torbi_b200.MIN_CHUNK_SIZE == 32
+        assert not hasattr(torbi_b200, 'NOT_A_CONSTANT')
+        loader = torbi_b200.data.loader(['x.pt'])
+        assert loader.batch_size == 64
+    finally:
+        torbi_b200.BATCH_SIZE, torbi_b200.MIN_CHUNK_SIZE = 512, None
+
+
+def test_product_never_imports_the_oracle():
+    # the oracle is test infrastructure: nothing under torbi_b200/ may reference it
+    for path in (ROOT / 'torbi_b200').rglob('*'):
+        if path.suffix in ('.py', '.cu', '.cuh', '.h'):
+            text = path.read_text()
+            assert 'oracle' not in text.lower(), path

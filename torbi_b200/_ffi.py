@@ -20,6 +20,7 @@ OBS_IS_PROBABILITY = 1 << 0
 EPS_FLOOR = 1 << 1
 FORCE_GENERIC = 1 << 8
 FORCE_TILED = 1 << 9
+TIME_KERNELS = 1 << 10
 
 ABI_VERSION = 1
 
@@ -40,6 +41,7 @@ SIGNATURES = {
     'torbi_b200_release': (None, []),
     'torbi_b200_launch_count': (ctypes.c_uint64, []),
     'torbi_b200_last_kernel': (ctypes.c_char_p, []),
+    'torbi_b200_last_timing': (ctypes.c_int, [_p, _p]),
 }
 
 _lib = None

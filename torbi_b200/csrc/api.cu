@@ -26,6 +26,28 @@ thread_local char g_error[512] = "";
 thread_local const char *g_last_kernel = "none";
 std::atomic<uint64_t> g_launches{0};
 
+// events for TORBI_B200_TIME_KERNELS, per host thread, bound to one device
+struct TimingEvents {
+    int device = -1;
+    bool valid = false;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+};
+thread_local TimingEvents g_timing;
+
+cudaError_t timing_prepare(int device) {
+    if (g_timing.device == device && g_timing.ev[0]) return cudaSuccess;
+    for (auto &e : g_timing.ev) {
+        if (e) cudaEventDestroy(e);
+        e = nullptr;
+    }
+    for (auto &e : g_timing.ev) {
+        cudaError_t err = cudaEventCreate(&e);
+        if (err != cudaSuccess) return err;
+    }
+    g_timing.device = device;
+    return cudaSuccess;
+}
+
 int fail(int code, const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -168,6 +190,14 @@ int torbi_b200_decode(const float *observation, const int32_t *batch_frames,
     a.sm_count = info.sm_count;
     a.ws = ws;
 
+    const bool timed = flags & TORBI_B200_TIME_KERNELS;
+    g_timing.valid = false;
+    if (timed) {
+        e = timing_prepare(device);
+        if (e == cudaSuccess) e = cudaEventRecord(g_timing.ev[0], stream);
+        if (e != cudaSuccess) return fail_cuda(e, "timing events");
+    }
+
     bool tiled = forward_tiled_supported(a) && !(flags & TORBI_B200_FORCE_GENERIC);
     if ((flags & TORBI_B200_FORCE_TILED) && !tiled)
         return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "tiled kernel does not support this shape");
@@ -179,9 +209,28 @@ int torbi_b200_decode(const float *observation, const int32_t *batch_frames,
         g_last_kernel = "forward_generic";
     }
     if (e != cudaSuccess) return fail_cuda(e, g_last_kernel);
+    if (timed) cudaEventRecord(g_timing.ev[1], stream);
     e = launch_backtrace(ws, indices, B, T, S, stream);
     if (e != cudaSuccess) return fail_cuda(e, "backtrace");
+    if (timed) {
+        cudaEventRecord(g_timing.ev[2], stream);
+        g_timing.valid = true;
+    }
     g_launches += 2;
+    return TORBI_B200_OK;
+}
+
+int torbi_b200_last_timing(float *forward_ms, float *backtrace_ms) {
+    if (!g_timing.valid)
+        return fail(TORBI_B200_ERR_INVALID_ARGUMENT,
+                    "no decode with TORBI_B200_TIME_KERNELS on this thread");
+    cudaError_t e = cudaEventSynchronize(g_timing.ev[2]);
+    float fwd = 0.f, back = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&fwd, g_timing.ev[0], g_timing.ev[1]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&back, g_timing.ev[1], g_timing.ev[2]);
+    if (e != cudaSuccess) return fail_cuda(e, "timing events");
+    if (forward_ms) *forward_ms = fwd;
+    if (backtrace_ms) *backtrace_ms = back;
     return TORBI_B200_OK;
 }
 

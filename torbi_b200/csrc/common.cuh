@@ -47,8 +47,8 @@ struct Workspace {
     int32_t *order;         // (B,)  items sorted by length, longest first
     int32_t *final_state;   // (B,)  argmax of the final forward scores
     uint32_t *sync;         // scheduling / barrier words (zeroed per call)
-    float *score[2];        // ping-pong forward scores, (B_pad, S_pad) each
-    float *transition_pad;  // (S_pad, S_pad) -inf padded copy when S % 32 != 0, else unused
+    float *score[2];        // ping-pong forward scores, (pad_batch, padded_sources) each
+    float *transition_pad;  // (padded_dests, padded_sources) copy, -inf outside (S,S)
     uint16_t *backptr;      // (B, T, S) uint16 backpointers; row 0 unused
     size_t bytes;
 };
@@ -57,7 +57,14 @@ constexpr size_t kSyncWords = 4096;
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-inline int64_t pad_states(int64_t S) { return (S + 31) / 32 * 32; }
+// Tiling constants of forward_tiled.cu that fix the padded layouts.
+constexpr int kTileDests = 80;     // destination states per CTA
+constexpr int kStageSources = 96;  // source states per pipeline stage
+
+// row length of the score buffers and of the padded transition copy
+inline int64_t padded_sources(int64_t S) { return (S + kStageSources - 1) / kStageSources * kStageSources; }
+// rows of the padded transition copy
+inline int64_t padded_dests(int64_t S) { return (S + kTileDests - 1) / kTileDests * kTileDests; }
 inline int64_t pad_batch(int64_t B) { return (B + 127) / 128 * 128; }
 
 inline Workspace carve_workspace(void *base, int64_t B, int64_t T, int64_t S) {
@@ -68,14 +75,14 @@ inline Workspace carve_workspace(void *base, int64_t B, int64_t T, int64_t S) {
         off += align_up(bytes, 256);
         return p;
     };
-    const int64_t Sp = pad_states(S), Bp = pad_batch(B);
+    const int64_t Sp = padded_sources(S), Bp = pad_batch(B);
     w.frames = static_cast<int32_t *>(take(sizeof(int32_t) * B));
     w.order = static_cast<int32_t *>(take(sizeof(int32_t) * Bp));
     w.final_state = static_cast<int32_t *>(take(sizeof(int32_t) * B));
     w.sync = static_cast<uint32_t *>(take(sizeof(uint32_t) * kSyncWords));
     w.score[0] = static_cast<float *>(take(sizeof(float) * Bp * Sp));
     w.score[1] = static_cast<float *>(take(sizeof(float) * Bp * Sp));
-    w.transition_pad = static_cast<float *>(take(sizeof(float) * Sp * Sp));
+    w.transition_pad = static_cast<float *>(take(sizeof(float) * padded_dests(S) * Sp));
     w.backptr = static_cast<uint16_t *>(take(sizeof(uint16_t) * B * T * S));
     w.bytes = off;
     return w;

@@ -130,7 +130,7 @@ static cudaError_t launch_generic_t(const ForwardArgs &a, cudaStream_t stream) {
     }
     kernel<<<(unsigned)a.B, kGenericThreads, smem, stream>>>(
         a.observation, a.ws.frames, a.transition, a.initial, a.ws.score[0], a.ws.score[1],
-        a.ws.backptr, a.posterior, a.ws.final_state, a.T, (int)a.S, pad_states(a.S), in_smem);
+        a.ws.backptr, a.posterior, a.ws.final_state, a.T, (int)a.S, padded_sources(a.S), in_smem);
     return cudaGetLastError();
 }
 

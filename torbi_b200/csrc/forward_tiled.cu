@@ -1,7 +1,421 @@
-// placeholder until the batch-tiled kernel lands
+// Batch-tiled forward kernel: the max-plus (tropical) product
+//     V[b][j] = max_s ( P[b][s] + A[j][s] ),  argmax with lowest-s ties
+// done as a register-tiled "GEMM" per timestep on the FP32/ALU pipes (FADD2 +
+// 3-input FMNMX; not tensor cores -- max-plus is not a multiply-add contraction).
+//
+// Work decomposition (persistent, cooperative launch, one CTA per SM):
+//   * sequences are processed longest-first in batches of TM = 64;
+//   * a GROUP of NJT = ceil(S / TN) CTAs owns one batch at a time; CTA `jt` of the
+//     group owns the TN = 80 destination states [jt*TN, jt*TN+TN) for all T steps;
+//   * per step every CTA streams its A slice [TN x S] and the batch's previous
+//     scores P[TM x S] from L2 through a 3-stage cp.async ring (96 source states
+//     per stage), so A is re-read once per 64 sequences instead of once per
+//     sequence as in the reference kernel (viterbi.cu:91,97);
+//   * the new scores are published to global memory (L2) and the group meets at
+//     a counter barrier; groups never wait for each other.
+//
+// Exactness (see DESIGN.md "Numerics"): every candidate is the single fp32 add
+// P[s] + A[j][s]; max is order independent; the argmax is found in two levels --
+// per 32-wide chunk of source states a strict `>` against the running maximum
+// records the FIRST chunk attaining the final maximum, then that chunk is
+// re-scanned for the lowest s with P[s] + A[j][s] == max.  This reproduces the
+// reference's ascending strict-`>` scan (viterbi.cpp:94-101) bit for bit.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
+
 namespace torbi_b200 {
-bool forward_tiled_supported(const ForwardArgs &) { return false; }
-cudaError_t launch_forward_tiled(const ForwardArgs &, cudaStream_t) { return cudaErrorNotSupported; }
+
+namespace {
+
+constexpr int TM = 64;          // sequences per batch (rows of the tile)
+constexpr int TN = kTileDests;  // destination states per CTA (columns of the tile)
+constexpr int KC = 32;          // source states per argmax chunk
+constexpr int KS = kStageSources;  // source states per pipeline stage (3 chunks)
+constexpr int LDS_ = KS + 4;    // smem row stride in floats: rows 4 banks apart
+constexpr int NSTAGE = 3;
+constexpr int kThreads = 256;
+constexpr int M = 4, N = 5;     // register tile: 4 sequences x 5 destination states
+constexpr int LANES_B = 8, LANES_J = 4, WARPS_J = 4;
+
+constexpr int kStageFloats = (TM + TN) * LDS_;
+constexpr size_t kSmemBytes =
+    sizeof(float) * (NSTAGE * kStageFloats + TM * TN)   // ring + emission/score tile
+    + sizeof(uint16_t) * TM * TN                        // backpointer tile
+    + sizeof(int) * 2 * TM;                             // per-slot item id and length
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {     // two fp32 adds (FADD2), IEEE rn
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float lo(u64 v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    // .cg: L2 only -- the score buffers are rewritten every step by other SMs
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kPending));
+}
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// All CTAs of a group have published their stores before any of them goes on.
+__device__ __forceinline__ void group_barrier(unsigned *counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (ld_acquire(counter) < target) {}
+    }
+    __syncthreads();
+}
+
+struct TiledParams {
+    const float *observation;   // (B,T,S)
+    const float *transition;    // padded copy (SJ, LDP), -inf outside (S,S)
+    const float *initial;       // (S,)
+    const int32_t *frames;      // (B,)
+    const int32_t *order;       // (Bpad,) items longest first, -1 = empty slot
+    float *score[2];            // (Bpad, LDP) ping-pong, row = position in `order`
+    uint16_t *backptr;          // (B,T,S)
+    float *posterior;           // (B,S) or null
+    int32_t *final_state;       // (B,)
+    unsigned *sync;             // one counter per group
+    int64_t T;
+    int S, LDP, NJT, NG, num_batches;
+};
+
+// issue the cp.async copies of one pipeline stage (source states [k0, k0+KS))
+__device__ __forceinline__ void load_stage_A(const TiledParams &p, float *stage, int j0, int k0) {
+    float *As = stage + TM * LDS_;
+    for (int idx = threadIdx.x; idx < TN * (KS / 4); idx += kThreads) {
+        const int row = idx / (KS / 4), c4 = idx % (KS / 4);
+        cp_async16(As + row * LDS_ + c4 * 4,
+                   p.transition + (int64_t)(j0 + row) * p.LDP + k0 + c4 * 4);
+    }
+}
+__device__ __forceinline__ void load_stage_P(const TiledParams &p, float *stage,
+                                             const float *score, int64_t row0, int k0) {
+    for (int idx = threadIdx.x; idx < TM * (KS / 4); idx += kThreads) {
+        const int row = idx / (KS / 4), c4 = idx % (KS / 4);
+        cp_async16(stage + row * LDS_ + c4 * 4, score + (row0 + row) * p.LDP + k0 + c4 * 4);
+    }
+}
+
+template <uint32_t kFlags>
+__global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledParams p) {
+    extern __shared__ __align__(16) float smem[];
+    float *ring = smem;
+    float *tile = smem + NSTAGE * kStageFloats;                      // [TM][TN] emission -> new score
+    uint16_t *bp_tile = reinterpret_cast<uint16_t *>(tile + TM * TN);  // [TM][TN]
+    int *slot_item = reinterpret_cast<int *>(bp_tile + TM * TN);       // [TM]
+    int *slot_frames = slot_item + TM;                                 // [TM]
+
+    const int group = blockIdx.x / p.NJT, jt = blockIdx.x % p.NJT;
+    if (group >= p.NG) return;
+    const int j0 = jt * TN;
+    unsigned *counter = p.sync + group * 32;                           // own 128-byte line
+    unsigned barriers = 0;
+
+    const int tid = threadIdx.x, lane = tid % kWarp, warp = tid / kWarp;
+    const int wb = warp / WARPS_J, wj = warp % WARPS_J;
+    const int lane_b = lane / LANES_J, lane_j = lane % LANES_J;
+    const int r_base = wb * (LANES_B * M) + lane_b;     // rows r_base + 8*i
+    const int c_base = wj * (LANES_J * N) + lane_j;     // cols c_base + 4*c
+    const int S = p.S, LDP = p.LDP;
+    const int nstages = LDP / KS;
+    const bool obs_vec = (S % 4) == 0 && (reinterpret_cast<uintptr_t>(p.observation) & 15) == 0;
+    const bool bp_vec = (S % 8) == 0;
+
+    for (int batch = group; batch < p.num_batches; batch += p.NG) {
+        const int64_t row0 = (int64_t)batch * TM;
+        __syncthreads();
+        if (tid < TM) {
+            const int item = p.order[row0 + tid];
+            slot_item[tid] = item;
+            slot_frames[tid] = item >= 0 ? p.frames[item] : 0;
+        }
+        __syncthreads();
+        const int batch_frames = slot_frames[0];        // longest first
+
+        // ---- t = 0: P_0[s] = obs[0][s] + initial[s]   (viterbi.cpp:72-76) ----
+        {
+            const int c_end = (jt == p.NJT - 1) ? LDP : min(j0 + TN, LDP);
+            for (int r = warp; r < TM; r += kThreads / kWarp) {
+                const int item = slot_item[r];
+                float *dst0 = p.score[0] + (row0 + r) * LDP;
+                float *dst1 = p.score[1] + (row0 + r) * LDP;
+                const float *obs = p.observation + (int64_t)max(item, 0) * p.T * S;
+                for (int c = j0 + lane; c < c_end; c += kWarp) {
+                    if (item >= 0 && c < S) {
+                        dst0[c] = convert_observation<kFlags>(obs[c]) + p.initial[c];
+                    } else {
+                        dst0[c] = 0.f;                   // padding stays finite, in both buffers
+                        dst1[c] = 0.f;
+                    }
+                }
+            }
+        }
+        barriers += p.NJT;
+        group_barrier(counter, barriers);
+
+        for (int t = 1; t < batch_frames; ++t) {
+            const float *P_cur = p.score[(t - 1) & 1];
+            float *P_new = p.score[t & 1];
+
+            // emission tile for this step (raw; converted when consumed)
+            if (obs_vec) {
+                for (int idx = tid; idx < TM * (TN / 4); idx += kThreads) {
+                    const int r = idx / (TN / 4), c4 = idx % (TN / 4);
+                    const int item = slot_item[r];
+                    if (item >= 0 && t < slot_frames[r] && j0 + c4 * 4 < S)
+                        cp_async16(tile + r * TN + c4 * 4,
+                                   p.observation + ((int64_t)item * p.T + t) * S + j0 + c4 * 4);
+                }
+            } else {
+                for (int idx = tid; idx < TM * TN; idx += kThreads) {
+                    const int r = idx / TN, c = idx % TN;
+                    const int item = slot_item[r];
+                    if (item >= 0 && t < slot_frames[r] && j0 + c < S)
+                        tile[idx] = __ldg(p.observation + ((int64_t)item * p.T + t) * S + j0 + c);
+                }
+            }
+            // prologue: stages 0 and 1
+            load_stage_A(p, ring, j0, 0);
+            load_stage_P(p, ring, P_cur, row0, 0);
+            cp_async_commit();
+            if (nstages > 1) {
+                load_stage_A(p, ring + kStageFloats, j0, KS);
+                load_stage_P(p, ring + kStageFloats, P_cur, row0, KS);
+            }
+            cp_async_commit();
+
+            float cur[M][N];
+            int bestc[M][N];
+#pragma unroll
+            for (int i = 0; i < M; ++i)
+#pragma unroll
+                for (int c = 0; c < N; ++c) { cur[i][c] = -INFINITY; bestc[i][c] = 0; }
+
+            for (int s = 0; s < nstages; ++s) {
+                cp_async_wait<1>();
+                __syncthreads();            // stage s landed; everyone is done with stage s-1
+                if (s + 2 < nstages) {
+                    float *dst = ring + ((s + 2) % NSTAGE) * kStageFloats;
+                    load_stage_A(p, dst, j0, (s + 2) * KS);
+                    load_stage_P(p, dst, P_cur, row0, (s + 2) * KS);
+                }
+                cp_async_commit();
+
+                const float *Ps = ring + (s % NSTAGE) * kStageFloats + r_base * LDS_;
+                const float *As = ring + (s % NSTAGE) * kStageFloats + (TM + c_base) * LDS_;
+#pragma unroll
+                for (int ch = 0; ch < KS / KC; ++ch) {
+                    float acc[M][N];
+#pragma unroll
+                    for (int k = 0; k < KC; k += 4) {
+                        ulonglong2 pv[M], av[N];
+#pragma unroll
+                        for (int i = 0; i < M; ++i)
+                            pv[i] = *reinterpret_cast<const ulonglong2 *>(Ps + i * LANES_B * LDS_ + ch * KC + k);
+#pragma unroll
+                        for (int c = 0; c < N; ++c)
+                            av[c] = *reinterpret_cast<const ulonglong2 *>(As + c * LANES_J * LDS_ + ch * KC + k);
+#pragma unroll
+                        for (int i = 0; i < M; ++i)
+#pragma unroll
+                            for (int c = 0; c < N; ++c) {
+                                const u64 v0 = add2(pv[i].x, av[c].x);
+                                const u64 v1 = add2(pv[i].y, av[c].y);
+                                // first group of the chunk reads `cur`, writes a fresh `acc`
+                                const float a0 = (k == 0) ? cur[i][c] : acc[i][c];
+                                acc[i][c] = fmaxf(fmaxf(fmaxf(fmaxf(a0, lo(v0)), hi(v0)), lo(v1)), hi(v1));
+                            }
+                    }
+                    const int chunk = s * (KS / KC) + ch;
+#pragma unroll
+                    for (int i = 0; i < M; ++i)
+#pragma unroll
+                        for (int c = 0; c < N; ++c) {
+                            if (acc[i][c] > cur[i][c]) bestc[i][c] = chunk;   // first chunk reaching the max
+                            cur[i][c] = acc[i][c];
+                        }
+                }
+            }
+            cp_async_wait<0>();     // the emission tile (first group) is long since in
+
+            // ---- exact argmax: lowest s in the winning chunk with P[s]+A[j][s] == max ----
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                const int r = r_base + i * LANES_B;
+                const bool live = t < slot_frames[r];
+                const float *Prow = P_cur + (row0 + r) * LDP;
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    const int col = c_base + c * LANES_J, j = j0 + col;
+                    if (live && j < S) {
+                        const float best = cur[i][c];
+                        const int k0 = bestc[i][c] * KC;
+                        const float4 *pp = reinterpret_cast<const float4 *>(Prow + k0);
+                        const float4 *ap = reinterpret_cast<const float4 *>(p.transition + (int64_t)j * LDP + k0);
+                        int arg = KC;
+#pragma unroll
+                        for (int q = KC / 4 - 1; q >= 0; --q) {
+                            const float4 pv = __ldcg(pp + q);
+                            const float4 av = __ldg(ap + q);
+                            if (pv.w + av.w == best) arg = 4 * q + 3;
+                            if (pv.z + av.z == best) arg = 4 * q + 2;
+                            if (pv.y + av.y == best) arg = 4 * q + 1;
+                            if (pv.x + av.x == best) arg = 4 * q;
+                        }
+                        // (arg == KC only for NaN input, outside the parity contract)
+                        bp_tile[r * TN + col] = (uint16_t)min(k0 + arg, S - 1);
+                        const float emit = convert_observation<kFlags>(tile[r * TN + col]);
+                        tile[r * TN + col] = emit + best;                       // viterbi.cpp:102
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- publish: new scores (frozen rows carried over) + uint16 backpointers ----
+            for (int idx = tid; idx < TM * (TN / 4); idx += kThreads) {
+                const int r = idx / (TN / 4), c4 = idx % (TN / 4);
+                const int col = j0 + c4 * 4;
+                if (col >= S || slot_item[r] < 0) continue;       // padding never changes
+                const int64_t off = (row0 + r) * LDP + col;
+                const bool live = t < slot_frames[r];              // finished rows are carried over
+                if (col + 3 < S) {
+                    const float4 v = live ? *reinterpret_cast<const float4 *>(tile + r * TN + c4 * 4)
+                                          : __ldcg(reinterpret_cast<const float4 *>(P_cur + off));
+                    *reinterpret_cast<float4 *>(P_new + off) = v;
+                } else {
+                    for (int e = 0; col + e < S; ++e)
+                        P_new[off + e] = live ? tile[r * TN + c4 * 4 + e] : __ldcg(P_cur + off + e);
+                }
+            }
+            if (bp_vec) {
+                for (int idx = tid; idx < TM * (TN / 8); idx += kThreads) {
+                    const int r = idx / (TN / 8), c8 = idx % (TN / 8);
+                    if (t < slot_frames[r] && j0 + c8 * 8 < S)
+                        *reinterpret_cast<uint4 *>(p.backptr + ((int64_t)slot_item[r] * p.T + t) * S + j0 + c8 * 8) =
+                            *reinterpret_cast<const uint4 *>(bp_tile + r * TN + c8 * 8);
+                }
+            } else {
+                for (int idx = tid; idx < TM * TN; idx += kThreads) {
+                    const int r = idx / TN, c = idx % TN;
+                    if (t < slot_frames[r] && j0 + c < S)
+                        p.backptr[((int64_t)slot_item[r] * p.T + t) * S + j0 + c] = bp_tile[idx];
+                }
+            }
+            barriers += p.NJT;
+            group_barrier(counter, barriers);
+        }
+
+        // ---- final scores out (viterbi.cpp:111-113) + first-occurrence argmax (:218) ----
+        const float *P_fin = p.score[(batch_frames - 1) & 1];
+        for (int r = jt * (kThreads / kWarp) + warp; r < TM; r += p.NJT * (kThreads / kWarp)) {
+            const int item = slot_item[r];
+            if (item < 0) continue;
+            const float *row = P_fin + (row0 + r) * LDP;
+            float best = -INFINITY;
+            int arg = 0x7fffffff;
+            for (int s = lane; s < S; s += kWarp) {
+                const float v = __ldcg(row + s);
+                if (p.posterior) p.posterior[(int64_t)item * S + s] = v;
+                if (better(v, s, best, arg)) { best = v; arg = s; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float ov = __shfl_xor_sync(kFullMask, best, off);
+                const int oi = __shfl_xor_sync(kFullMask, arg, off);
+                if (better(ov, oi, best, arg)) { best = ov; arg = oi; }
+            }
+            if (lane == 0) p.final_state[item] = (arg == 0x7fffffff) ? 0 : arg;
+        }
+        // the next batch uses other score rows; no barrier needed here
+    }
+}
+
+// (S,S) -> (SJ, LDP) with -inf padding: padded sources never win, padded
+// destinations are computed and dropped
+__global__ void pad_transition_kernel(const float *__restrict__ src, float *__restrict__ dst,
+                                      int S, int SJ, int LDP) {
+    const int64_t n = (int64_t)SJ * LDP;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i / LDP), s = (int)(i % LDP);
+        dst[i] = (j < S && s < S) ? src[(int64_t)j * S + s] : -INFINITY;
+    }
+}
+
+}  // namespace
+
+static int64_t tiled_ldp(int64_t S) { return padded_sources(S); }
+static int64_t tiled_sj(int64_t S) { return padded_dests(S); }
+
+bool forward_tiled_supported(const ForwardArgs &a) {
+    const int64_t njt = tiled_sj(a.S) / TN;
+    return njt <= a.sm_count && a.ws.transition_pad != nullptr;
+}
+
+template <uint32_t kFlags>
+static cudaError_t launch_tiled_t(const ForwardArgs &a, cudaStream_t stream) {
+    TiledParams p{};
+    p.observation = a.observation;
+    p.transition = a.ws.transition_pad;
+    p.initial = a.initial;
+    p.frames = a.ws.frames;
+    p.order = a.ws.order;
+    p.score[0] = a.ws.score[0];
+    p.score[1] = a.ws.score[1];
+    p.backptr = a.ws.backptr;
+    p.posterior = a.posterior;
+    p.final_state = a.ws.final_state;
+    p.sync = a.ws.sync;
+    p.T = a.T;
+    p.S = (int)a.S;
+    p.LDP = (int)tiled_ldp(a.S);
+    const int SJ = (int)tiled_sj(a.S);
+    p.NJT = SJ / TN;
+    p.num_batches = (int)((a.B + TM - 1) / TM);
+    p.NG = std::min(a.sm_count / p.NJT, p.num_batches);
+    if (p.NG * 32 > (int)kSyncWords) return cudaErrorInvalidValue;
+
+    pad_transition_kernel<<<a.sm_count * 4, 256, 0, stream>>>(a.transition, a.ws.transition_pad,
+                                                              p.S, SJ, p.LDP);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+
+    auto kernel = forward_tiled_kernel<kFlags>;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    void *args[] = {(void *)&p};
+    // cooperative launch: all CTAs of a group must be co-resident for the
+    // per-step counter barrier; the launch fails instead of deadlocking
+    return cudaLaunchCooperativeKernel((void *)kernel, dim3(p.NG * p.NJT), dim3(kThreads), args,
+                                       kSmemBytes, stream);
+}
+
+cudaError_t launch_forward_tiled(const ForwardArgs &a, cudaStream_t stream) {
+    switch (a.flags & 3u) {
+        case 0: return launch_tiled_t<0>(a, stream);
+        case 1: return launch_tiled_t<1>(a, stream);
+        case 2: return launch_tiled_t<2>(a, stream);
+        default: return launch_tiled_t<3>(a, stream);
+    }
+}
+
 }  // namespace torbi_b200
