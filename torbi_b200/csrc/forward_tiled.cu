@@ -41,9 +41,12 @@ constexpr int LANES_B = 8, LANES_J = 4, WARPS_J = 4;
 
 constexpr int kStageFloats = (TM + TN) * LDS_;
 constexpr size_t kSmemBytes =
-    sizeof(float) * (NSTAGE * kStageFloats + TM * TN)   // ring + emission/score tile
-    + sizeof(uint16_t) * TM * TN                        // backpointer tile
-    + sizeof(int) * 2 * TM;                             // per-slot item id and length
+    sizeof(float) * (NSTAGE * kStageFloats + 2 * TM * TN)  // ring + emission/score tile + max tile
+    + sizeof(uint16_t) * TM * TN                           // winning chunk -> backpointer tile
+    + sizeof(int) * 2 * TM;                                // per-slot item id and length
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+constexpr int kLoaders = 240;                 // 24 float4 columns x 10 rows per pass
+static_assert(KS / 4 == 24 && TN % 10 == 0, "loader mapping");
 
 typedef unsigned long long u64;
 
@@ -72,12 +75,17 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
     return v;
 }
 
-// All CTAs of a group have published their stores before any of them goes on.
-__device__ __forceinline__ void group_barrier(unsigned *counter, unsigned target) {
+// Group barrier in two halves so independent work can sit between them:
+// arrive = "my stores of this step are published", wait = "everyone's are".
+__device__ __forceinline__ void group_arrive(unsigned *counter) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(counter, 1u);
+    }
+}
+__device__ __forceinline__ void group_wait(const unsigned *counter, unsigned target) {
+    if (threadIdx.x == 0) {
         while (ld_acquire(counter) < target) {}
     }
     __syncthreads();
@@ -89,7 +97,7 @@ struct TiledParams {
     const float *initial;       // (S,)
     const int32_t *frames;      // (B,)
     const int32_t *order;       // (Bpad,) items longest first, -1 = empty slot
-    float *score[2];            // (Bpad, LDP) ping-pong, row = position in `order`
+    float *score[3];            // (Bpad, LDP) rotating buffers, row = position in `order`
     uint16_t *backptr;          // (B,T,S)
     float *posterior;           // (B,S) or null
     int32_t *final_state;       // (B,)
@@ -98,20 +106,20 @@ struct TiledParams {
     int S, LDP, NJT, NG, num_batches;
 };
 
-// issue the cp.async copies of one pipeline stage (source states [k0, k0+KS))
-__device__ __forceinline__ void load_stage_A(const TiledParams &p, float *stage, int j0, int k0) {
-    float *As = stage + TM * LDS_;
-    for (int idx = threadIdx.x; idx < TN * (KS / 4); idx += kThreads) {
-        const int row = idx / (KS / 4), c4 = idx % (KS / 4);
-        cp_async16(As + row * LDS_ + c4 * 4,
-                   p.transition + (int64_t)(j0 + row) * p.LDP + k0 + c4 * 4);
-    }
-}
-__device__ __forceinline__ void load_stage_P(const TiledParams &p, float *stage,
-                                             const float *score, int64_t row0, int k0) {
-    for (int idx = threadIdx.x; idx < TM * (KS / 4); idx += kThreads) {
-        const int row = idx / (KS / 4), c4 = idx % (KS / 4);
-        cp_async16(stage + row * LDS_ + c4 * 4, score + (row0 + row) * p.LDP + k0 + c4 * 4);
+// Issue the cp.async copies of one pipeline stage.  Thread `tid` < 240 owns the
+// float4 column tid % 24 of rows tid / 24 + 10*q, so every address is a fixed
+// per-thread base plus a constant stride: no divisions in the loop.
+__device__ __forceinline__ void load_stage(float *stage, const float *gA, const float *gP,
+                                           int64_t row_stride10, int r0) {
+    if (threadIdx.x < kLoaders) {
+        float *sP = stage, *sA = stage + TM * LDS_;
+#pragma unroll
+        for (int q = 0; q < TN / 10; ++q)
+            cp_async16(sA + q * 10 * LDS_, gA + q * row_stride10);
+#pragma unroll
+        for (int q = 0; q < (TM + 9) / 10; ++q)
+            if (q * 10 + 9 < TM || r0 + q * 10 < TM)
+                cp_async16(sP + q * 10 * LDS_, gP + q * row_stride10);
     }
 }
 
@@ -120,7 +128,8 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
     extern __shared__ __align__(16) float smem[];
     float *ring = smem;
     float *tile = smem + NSTAGE * kStageFloats;                      // [TM][TN] emission -> new score
-    uint16_t *bp_tile = reinterpret_cast<uint16_t *>(tile + TM * TN);  // [TM][TN]
+    float *best_tile = tile + TM * TN;                               // [TM][TN] max over sources
+    uint16_t *bp_tile = reinterpret_cast<uint16_t *>(best_tile + TM * TN);  // [TM][TN] chunk, then index
     int *slot_item = reinterpret_cast<int *>(bp_tile + TM * TN);       // [TM]
     int *slot_frames = slot_item + TM;                                 // [TM]
 
@@ -139,6 +148,11 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
     const int nstages = LDP / KS;
     const bool obs_vec = (S % 4) == 0 && (reinterpret_cast<uintptr_t>(p.observation) & 15) == 0;
     const bool bp_vec = (S % 8) == 0;
+    // loader mapping (see load_stage)
+    const int ld_c4 = tid % (KS / 4), ld_r0 = tid / (KS / 4);
+    const int ld_smem = ld_r0 * LDS_ + ld_c4 * 4;
+    const float *ld_A = p.transition + (int64_t)(j0 + ld_r0) * LDP + ld_c4 * 4;
+    const int64_t ld_stride10 = (int64_t)10 * LDP;
 
     for (int batch = group; batch < p.num_batches; batch += p.NG) {
         const int64_t row0 = (int64_t)batch * TM;
@@ -158,23 +172,29 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                 const int item = slot_item[r];
                 float *dst0 = p.score[0] + (row0 + r) * LDP;
                 float *dst1 = p.score[1] + (row0 + r) * LDP;
+                float *dst2 = p.score[2] + (row0 + r) * LDP;
                 const float *obs = p.observation + (int64_t)max(item, 0) * p.T * S;
                 for (int c = j0 + lane; c < c_end; c += kWarp) {
                     if (item >= 0 && c < S) {
                         dst0[c] = convert_observation<kFlags>(obs[c]) + p.initial[c];
                     } else {
-                        dst0[c] = 0.f;                   // padding stays finite, in both buffers
+                        dst0[c] = 0.f;                   // padding stays finite, in all buffers
                         dst1[c] = 0.f;
+                        dst2[c] = 0.f;
                     }
                 }
             }
         }
         barriers += p.NJT;
-        group_barrier(counter, barriers);
+        group_arrive(counter);
+        group_wait(counter, barriers);
 
         for (int t = 1; t < batch_frames; ++t) {
-            const float *P_cur = p.score[(t - 1) & 1];
-            float *P_new = p.score[t & 1];
+            // three rotating buffers: a CTA that is already publishing step t+1 never
+            // writes the buffer a slower CTA of the group still re-scans for step t
+            const float *P_cur = p.score[(t - 1) % 3];
+            float *P_new = p.score[t % 3];
+            const float *ld_P = P_cur + (row0 + ld_r0) * LDP + ld_c4 * 4;
 
             // emission tile for this step (raw; converted when consumed)
             if (obs_vec) {
@@ -194,13 +214,10 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                 }
             }
             // prologue: stages 0 and 1
-            load_stage_A(p, ring, j0, 0);
-            load_stage_P(p, ring, P_cur, row0, 0);
+            load_stage(ring + ld_smem, ld_A, ld_P, ld_stride10, ld_r0);
             cp_async_commit();
-            if (nstages > 1) {
-                load_stage_A(p, ring + kStageFloats, j0, KS);
-                load_stage_P(p, ring + kStageFloats, P_cur, row0, KS);
-            }
+            if (nstages > 1)
+                load_stage(ring + kStageFloats + ld_smem, ld_A + KS, ld_P + KS, ld_stride10, ld_r0);
             cp_async_commit();
 
             float cur[M][N];
@@ -213,11 +230,9 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             for (int s = 0; s < nstages; ++s) {
                 cp_async_wait<1>();
                 __syncthreads();            // stage s landed; everyone is done with stage s-1
-                if (s + 2 < nstages) {
-                    float *dst = ring + ((s + 2) % NSTAGE) * kStageFloats;
-                    load_stage_A(p, dst, j0, (s + 2) * KS);
-                    load_stage_P(p, dst, P_cur, row0, (s + 2) * KS);
-                }
+                if (s + 2 < nstages)
+                    load_stage(ring + ((s + 2) % NSTAGE) * kStageFloats + ld_smem,
+                               ld_A + (s + 2) * KS, ld_P + (s + 2) * KS, ld_stride10, ld_r0);
                 cp_async_commit();
 
                 const float *Ps = ring + (s % NSTAGE) * kStageFloats + r_base * LDS_;
@@ -257,46 +272,32 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             }
             cp_async_wait<0>();     // the emission tile (first group) is long since in
 
-            // ---- exact argmax: lowest s in the winning chunk with P[s]+A[j][s] == max ----
+            // ---- new scores: obs[t][j] + max  (viterbi.cpp:102); keep max and winning chunk ----
 #pragma unroll
             for (int i = 0; i < M; ++i) {
                 const int r = r_base + i * LANES_B;
-                const bool live = t < slot_frames[r];
-                const float *Prow = P_cur + (row0 + r) * LDP;
+                if (t < slot_frames[r]) {
 #pragma unroll
-                for (int c = 0; c < N; ++c) {
-                    const int col = c_base + c * LANES_J, j = j0 + col;
-                    if (live && j < S) {
-                        const float best = cur[i][c];
-                        const int k0 = bestc[i][c] * KC;
-                        const float4 *pp = reinterpret_cast<const float4 *>(Prow + k0);
-                        const float4 *ap = reinterpret_cast<const float4 *>(p.transition + (int64_t)j * LDP + k0);
-                        int arg = KC;
-#pragma unroll
-                        for (int q = KC / 4 - 1; q >= 0; --q) {
-                            const float4 pv = __ldcg(pp + q);
-                            const float4 av = __ldg(ap + q);
-                            if (pv.w + av.w == best) arg = 4 * q + 3;
-                            if (pv.z + av.z == best) arg = 4 * q + 2;
-                            if (pv.y + av.y == best) arg = 4 * q + 1;
-                            if (pv.x + av.x == best) arg = 4 * q;
+                    for (int c = 0; c < N; ++c) {
+                        const int col = c_base + c * LANES_J;
+                        if (j0 + col < S) {
+                            const float emit = convert_observation<kFlags>(tile[r * TN + col]);
+                            tile[r * TN + col] = emit + cur[i][c];
+                            best_tile[r * TN + col] = cur[i][c];
+                            bp_tile[r * TN + col] = (uint16_t)bestc[i][c];
                         }
-                        // (arg == KC only for NaN input, outside the parity contract)
-                        bp_tile[r * TN + col] = (uint16_t)min(k0 + arg, S - 1);
-                        const float emit = convert_observation<kFlags>(tile[r * TN + col]);
-                        tile[r * TN + col] = emit + best;                       // viterbi.cpp:102
                     }
                 }
             }
             __syncthreads();
 
-            // ---- publish: new scores (frozen rows carried over) + uint16 backpointers ----
+            // ---- publish the new scores (finished rows are carried over), then arrive ----
             for (int idx = tid; idx < TM * (TN / 4); idx += kThreads) {
                 const int r = idx / (TN / 4), c4 = idx % (TN / 4);
                 const int col = j0 + c4 * 4;
                 if (col >= S || slot_item[r] < 0) continue;       // padding never changes
                 const int64_t off = (row0 + r) * LDP + col;
-                const bool live = t < slot_frames[r];              // finished rows are carried over
+                const bool live = t < slot_frames[r];
                 if (col + 3 < S) {
                     const float4 v = live ? *reinterpret_cast<const float4 *>(tile + r * TN + c4 * 4)
                                           : __ldcg(reinterpret_cast<const float4 *>(P_cur + off));
@@ -306,6 +307,64 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                         P_new[off + e] = live ? tile[r * TN + c4 * 4 + e] : __ldcg(P_cur + off + e);
                 }
             }
+            barriers += p.NJT;
+            group_arrive(counter);
+
+            // ---- exact argmax while the rest of the group catches up: lowest s in the
+            //      winning chunk with P[s] + A[j][s] == max.  8 lanes share one output
+            //      (a float4 of the chunk each), so every load is a coalesced 128-byte row.
+            {
+                constexpr int kBatch = 10;                        // outputs in flight per lane group
+                const int sub = lane >> 3, q4 = (lane & 7) * 4;
+                for (int rr = 0; rr < TM / (kThreads / kWarp); ++rr) {
+                    const int r = warp * (TM / (kThreads / kWarp)) + rr;
+                    if (t >= slot_frames[r]) continue;            // warp-uniform
+                    const float *Prow = P_cur + (row0 + r) * LDP + q4;
+                    const float *Arow = p.transition + (int64_t)j0 * LDP + q4;
+#pragma unroll 1
+                    for (int cb = 0; cb < TN / 4; cb += kBatch) {
+                        float best[kBatch];
+                        int k0[kBatch];
+                        float4 pv[kBatch], av[kBatch];
+                        // all shared-memory reads, then all global loads, then the compares:
+                        // nothing in a batch waits on an earlier output's store
+#pragma unroll
+                        for (int u = 0; u < kBatch; ++u) {
+                            const int col = (cb + u) * 4 + sub;
+                            best[u] = best_tile[r * TN + col];
+                            k0[u] = bp_tile[r * TN + col] * KC;
+                        }
+#pragma unroll
+                        for (int u = 0; u < kBatch; ++u) {
+                            const int col = (cb + u) * 4 + sub;
+                            const bool valid = j0 + col < S;
+                            if (!valid) k0[u] = 0;                // stale tile entry: stay in bounds
+                            pv[u] = __ldcg(reinterpret_cast<const float4 *>(Prow + k0[u]));
+                            av[u] = __ldg(reinterpret_cast<const float4 *>(
+                                Arow + (int64_t)(valid ? col : 0) * LDP + k0[u]));
+                        }
+#pragma unroll
+                        for (int u = 0; u < kBatch; ++u) {
+                            const int col = (cb + u) * 4 + sub;
+                            unsigned key = 64;
+                            if (pv[u].w + av[u].w == best[u]) key = q4 + 3;
+                            if (pv[u].z + av[u].z == best[u]) key = q4 + 2;
+                            if (pv[u].y + av[u].y == best[u]) key = q4 + 1;
+                            if (pv[u].x + av[u].x == best[u]) key = q4;
+                            // min over the 8 lanes of the output (xor 1,2,4 stays inside the group)
+                            key = min(key, __shfl_xor_sync(kFullMask, key, 1));
+                            key = min(key, __shfl_xor_sync(kFullMask, key, 2));
+                            key = min(key, __shfl_xor_sync(kFullMask, key, 4));
+                            // (key == 64 only for NaN input, outside the parity contract)
+                            if ((lane & 7) == 0 && j0 + col < S)
+                                bp_tile[r * TN + col] = (uint16_t)min(k0[u] + (int)key, S - 1);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- backpointers: coalesced, vectorised uint16 stores ----
             if (bp_vec) {
                 for (int idx = tid; idx < TM * (TN / 8); idx += kThreads) {
                     const int r = idx / (TN / 8), c8 = idx % (TN / 8);
@@ -320,12 +379,11 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                         p.backptr[((int64_t)slot_item[r] * p.T + t) * S + j0 + c] = bp_tile[idx];
                 }
             }
-            barriers += p.NJT;
-            group_barrier(counter, barriers);
+            group_wait(counter, barriers);
         }
 
         // ---- final scores out (viterbi.cpp:111-113) + first-occurrence argmax (:218) ----
-        const float *P_fin = p.score[(batch_frames - 1) & 1];
+        const float *P_fin = p.score[(batch_frames - 1) % 3];
         for (int r = jt * (kThreads / kWarp) + warp; r < TM; r += p.NJT * (kThreads / kWarp)) {
             const int item = slot_item[r];
             if (item < 0) continue;
@@ -381,6 +439,7 @@ static cudaError_t launch_tiled_t(const ForwardArgs &a, cudaStream_t stream) {
     p.order = a.ws.order;
     p.score[0] = a.ws.score[0];
     p.score[1] = a.ws.score[1];
+    p.score[2] = a.ws.score[2];
     p.backptr = a.ws.backptr;
     p.posterior = a.posterior;
     p.final_state = a.ws.final_state;
