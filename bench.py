@@ -64,6 +64,21 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source='fallback (B200_PROFILING.md)')
 
 
+def profiled_traffic(kernel, args):
+    """DRAM bytes (read + write) of one launch of the forward kernel from the
+    committed `ncu --set full` capture of this same workload, or None."""
+    path = ROOT / 'profiles' / 'forward_tiled_ncu_full.json'
+    if kernel != 'forward_tiled' or not path.exists() or \
+            (args.batch, args.frames, args.states) != (512, 2000, 1440):
+        return None
+    m = json.loads(path.read_text())
+    scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
+    total = 0.0
+    for key in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+        total += float(m[key]['value'].replace(',', '')) * scale[m[key]['unit']]
+    return total
+
+
 def workload_config(args, world):
     return {
         'workload': 'BASELINE config 2: from_probabilities hot path, log-softmax(randn) observations, '
@@ -332,7 +347,8 @@ def bench_graft(args):
             'clocks': clocks.summary(),
             'roofline': {
                 'bound': 'fp32_alu_issue', 'kernel': kernel, 'achieved': achieved, 'peak': peak,
-                'unit': 'T lane-op/s', 'frac': achieved / peak, 'traffic': None,
+                'unit': 'T lane-op/s', 'frac': achieved / peak, 'traffic': profiled_traffic(kernel, args),
+                'traffic_note': 'DRAM read+write bytes per launch, ncu --set full capture in profiles/ (not live)',
                 'kernel_ms': kernel_ms, 'kernel_share_of_step': kernel_ms * args.steps / elapsed_ms,
                 'backtrace_ms': statistics.mean(back_ms),
                 'ops_per_launch': ops, 'peak_source': f"{sm_count} SMs x 128 lanes x {peaks['sm_max_mhz']} MHz, {peaks['source']}",
