@@ -84,13 +84,27 @@ inner_kernel(float *out, int chunks, int reps, long long *cycles) {
                             acc[i][c] = fmaxf(acc[i][c], hi(p[i].x) + hi(a[c].x));
                             acc[i][c] = fmaxf(acc[i][c], lo(p[i].y) + lo(a[c].y));
                             acc[i][c] = fmaxf(acc[i][c], hi(p[i].y) + hi(a[c].y));
-                        } else {
+                        } else if (MODE == 1) {
                             const u64 v0 = add2(p[i].x, a[c].x);
                             const u64 v1 = add2(p[i].y, a[c].y);
                             acc[i][c] = fmaxf(fmaxf(cur[i][c], lo(v0)), hi(v0));
                             acc[i][c] = fmaxf(fmaxf(acc[i][c], lo(v1)), hi(v1));
                         }
                     }
+                if (MODE == 2) {
+#pragma unroll
+                    for (int i = 0; i < M; ++i) {
+                        u64 v[N];
+#pragma unroll
+                        for (int c = 0; c < N; ++c) v[c] = add2(p[i].x, a[c].x);   // N adds share p[i].x
+#pragma unroll
+                        for (int c = 0; c < N; ++c) acc[i][c] = fmaxf(fmaxf(cur[i][c], lo(v[c])), hi(v[c]));
+#pragma unroll
+                        for (int c = 0; c < N; ++c) v[c] = add2(p[i].y, a[c].y);
+#pragma unroll
+                        for (int c = 0; c < N; ++c) acc[i][c] = fmaxf(fmaxf(acc[i][c], lo(v[c])), hi(v[c]));
+                    }
+                }
             }
 #pragma unroll kKUnroll
             for (int k = 4; k < KC; k += 4) {
@@ -110,13 +124,27 @@ inner_kernel(float *out, int chunks, int reps, long long *cycles) {
                             acc[i][c] = fmaxf(acc[i][c], hi(p[i].x) + hi(a[c].x));
                             acc[i][c] = fmaxf(acc[i][c], lo(p[i].y) + lo(a[c].y));
                             acc[i][c] = fmaxf(acc[i][c], hi(p[i].y) + hi(a[c].y));
-                        } else {
+                        } else if (MODE == 1) {
                             const u64 v0 = add2(p[i].x, a[c].x);
                             const u64 v1 = add2(p[i].y, a[c].y);
                             acc[i][c] = fmaxf(fmaxf(acc[i][c], lo(v0)), hi(v0));
                             acc[i][c] = fmaxf(fmaxf(acc[i][c], lo(v1)), hi(v1));
                         }
                     }
+                if (MODE == 2) {
+#pragma unroll
+                    for (int i = 0; i < M; ++i) {
+                        u64 v[N];
+#pragma unroll
+                        for (int c = 0; c < N; ++c) v[c] = add2(p[i].x, a[c].x);
+#pragma unroll
+                        for (int c = 0; c < N; ++c) acc[i][c] = fmaxf(fmaxf(acc[i][c], lo(v[c])), hi(v[c]));
+#pragma unroll
+                        for (int c = 0; c < N; ++c) v[c] = add2(p[i].y, a[c].y);
+#pragma unroll
+                        for (int c = 0; c < N; ++c) acc[i][c] = fmaxf(fmaxf(acc[i][c], lo(v[c])), hi(v[c]));
+                    }
+                }
             }
             // chunk end: strict improvement records the chunk id
 #pragma unroll
@@ -176,6 +204,11 @@ int main() {
     run<1, 4, 4, 8, 4, 2, 4>("packed 4x4 lanes8x4 warps2x4", sms);
     run<0, 4, 5, 8, 4, 2, 4>("scalar 4x5 lanes8x4 warps2x4", sms);
     run<1, 4, 5, 8, 4, 2, 4>("packed 4x5 lanes8x4 warps2x4", sms);
+    run<2, 4, 5, 8, 4, 2, 4>("reuse  4x5 lanes8x4 warps2x4", sms);
+    run<2, 4, 4, 8, 4, 2, 4>("reuse  4x4 lanes8x4 warps2x4", sms);
+    run<2, 8, 4, 8, 4, 2, 4>("reuse  8x4 lanes8x4 warps2x4", sms);
+    run<2, 4, 8, 8, 4, 2, 4>("reuse  4x8 lanes8x4 warps2x4", sms);
+    run<2, 5, 4, 4, 8, 4, 2>("reuse  5x4 lanes4x8 warps4x2", sms);
     run<1, 4, 5, 4, 8, 4, 2>("packed 4x5 lanes4x8 warps4x2", sms);
     run<1, 8, 4, 4, 8, 2, 4>("packed 8x4 lanes4x8 warps2x4", sms);
     run<1, 8, 4, 8, 4, 2, 4>("packed 8x4 lanes8x4 warps2x4", sms);

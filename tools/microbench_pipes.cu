@@ -13,7 +13,8 @@ constexpr int CH = 8;       // independent chains per thread
 constexpr int UNROLL = 16;  // ops per chain per loop trip
 
 enum Op { FMNMX, FMNMX3, IMIN_U32, VIMIN3_U32, FADD, FADD2, FSETP_SEL, FADD_FMNMX, FADD2_FMNMX3,
-          FADD2_2IMIN, FADD2_VIMIN3, FADD2_2FMNMX, FFMA, FADD2_VIMIN3_PLUS_FMNMX };
+          FADD2_2IMIN, FADD2_VIMIN3, FADD2_2FMNMX, FFMA, FADD2_VIMIN3_PLUS_FMNMX,
+          TWO_FADD_FMNMX3, MIX_FADD2_2FADD_2FMNMX3, FADD2_FMNMX3_SAMEOP, FADD2_SELF_FMNMX3, FADD2x2_FMNMX3x2 };
 
 template <int OP>
 __global__ void __launch_bounds__(512, 1) pipe_kernel(float *out, int trips, long long *cycles, float seed) {
@@ -47,6 +48,34 @@ __global__ void __launch_bounds__(512, 1) pipe_kernel(float *out, int trips, lon
                 if (OP == FADD_FMNMX) {
                     asm volatile("add.f32 %0, %0, %1;" : "+f"(y[i]) : "f"(seed));
                     asm volatile("max.f32 %0, %0, %1;" : "+f"(x[i]) : "f"(y[i]));
+                }
+                if (OP == TWO_FADD_FMNMX3) {
+                    asm volatile("add.f32 %0, %0, %1;" : "+f"(y[i]) : "f"(seed));
+                    asm volatile("add.f32 %0, %0, %1;" : "+f"(z[i]) : "f"(seed));
+                    asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(x[i]) : "f"(y[i]), "f"(z[i]));
+                }
+                if (OP == MIX_FADD2_2FADD_2FMNMX3) {   // 4 cells: one packed add, two scalar adds, two max3
+                    asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(w[i]) : "l"(cst));
+                    asm volatile("add.f32 %0, %0, %1;" : "+f"(y[i]) : "f"(seed));
+                    asm volatile("add.f32 %0, %0, %1;" : "+f"(z[i]) : "f"(seed));
+                    asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(x[i]) : "f"(__uint_as_float((unsigned)w[i])), "f"(__uint_as_float((unsigned)(w[i] >> 32))));
+                    asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(x[i]) : "f"(y[i]), "f"(z[i]));
+                }
+                if (OP == FADD2_FMNMX3_SAMEOP) {       // max3 reads only two distinct registers
+                    asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(w[i]) : "l"(cst));
+                    asm volatile("max.f32 %0, %0, %1, %1;" : "+f"(x[i]) : "f"(__uint_as_float((unsigned)w[i])));
+                }
+                if (OP == FADD2_SELF_FMNMX3) {         // packed add reads one pair twice
+                    asm volatile("add.rn.f32x2 %0, %0, %0;" : "+l"(w[i]));
+                    asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(x[i]) : "f"(__uint_as_float((unsigned)w[i])), "f"(__uint_as_float((unsigned)(w[i] >> 32))));
+                }
+                if (OP == FADD2x2_FMNMX3x2) {          // the real loop's shape: 2 adds feed 2 max3 on ONE accumulator
+                    u64 v0 = w[i], v1 = w[(i + 1) % CH];
+                    asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(v0) : "l"(w[i]), "l"(cst));
+                    asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(v1) : "l"(w[(i + 1) % CH]), "l"(cst));
+                    w[i] = v0;
+                    asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(x[i]) : "f"(__uint_as_float((unsigned)v0)), "f"(__uint_as_float((unsigned)(v0 >> 32))));
+                    asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(x[i]) : "f"(__uint_as_float((unsigned)v1)), "f"(__uint_as_float((unsigned)(v1 >> 32))));
                 }
                 if (OP == FADD2_FMNMX3 || OP == FADD2_2IMIN || OP == FADD2_VIMIN3 || OP == FADD2_2FMNMX || OP == FADD2_VIMIN3_PLUS_FMNMX) {
                     asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(w[i]) : "l"(cst));
@@ -167,6 +196,11 @@ int main() {
     run<FADD2_2IMIN>("FADD2 + 2 IMNMX.u32", 3, 2, sms);
     run<FADD2_VIMIN3>("FADD2 + VIMNMX3.u32", 2, 2, sms);
     run<FADD2_VIMIN3_PLUS_FMNMX>("FADD2 + alt(VIMNMX3,FMNMX3)", 2, 2, sms);
+    run<TWO_FADD_FMNMX3>("2 FADD + FMNMX3", 3, 2, sms);
+    run<MIX_FADD2_2FADD_2FMNMX3>("FADD2 + 2 FADD + 2 FMNMX3", 5, 4, sms);
+    run<FADD2_FMNMX3_SAMEOP>("FADD2 + FMNMX3(x,lo,lo)", 2, 2, sms);
+    run<FADD2_SELF_FMNMX3>("FADD2(w,w) + FMNMX3", 2, 2, sms);
+    run<FADD2x2_FMNMX3x2>("2 FADD2 + 2 FMNMX3 (1 acc)", 4, 4, sms);
     for (int d : {1, 2, 4, 8, 16, 32}) run_lds(d, 36, sms);
     run_lds(8, 32, sms);
     run_lds(8, 4, sms);

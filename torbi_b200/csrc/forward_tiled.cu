@@ -97,7 +97,8 @@ struct TiledParams {
     const float *initial;       // (S,)
     const int32_t *frames;      // (B,)
     const int32_t *order;       // (Bpad,) items longest first, -1 = empty slot
-    float *score[3];            // (Bpad, LDP) rotating buffers, row = position in `order`
+    float *score0;              // 3 rotating buffers (Bpad, LDP), `score_stride` floats apart;
+    int64_t score_stride;       // row = position in `order`
     uint16_t *backptr;          // (B,T,S)
     float *posterior;           // (B,S) or null
     int32_t *final_state;       // (B,)
@@ -107,19 +108,87 @@ struct TiledParams {
 };
 
 // Issue the cp.async copies of one pipeline stage.  Thread `tid` < 240 owns the
-// float4 column tid % 24 of rows tid / 24 + 10*q, so every address is a fixed
-// per-thread base plus a constant stride: no divisions in the loop.
-__device__ __forceinline__ void load_stage(float *stage, const float *gA, const float *gP,
-                                           int64_t row_stride10, int r0) {
+// float4 column tid % 24 of rows tid / 24 + 10*q (8 A rows + 7 P rows per thread),
+// so every address is a fixed per-thread base plus a constant stride.  The 15
+// copies are issued in three parts, one per argmax chunk, so they interleave
+// with the math instead of piling up in the load/store queue.
+template <int kPart>
+__device__ __forceinline__ void load_stage_part(float *stage, const float *gA, const float *gP,
+                                                int64_t row_stride10, int r0) {
     if (threadIdx.x < kLoaders) {
         float *sP = stage, *sA = stage + TM * LDS_;
 #pragma unroll
         for (int q = 0; q < TN / 10; ++q)
-            cp_async16(sA + q * 10 * LDS_, gA + q * row_stride10);
+            if (q / 5 == kPart)                                   // part 0: A rows q = 0..4, part 1: q = 5..7
+                cp_async16(sA + q * 10 * LDS_, gA + q * row_stride10);
 #pragma unroll
         for (int q = 0; q < (TM + 9) / 10; ++q)
-            if (q * 10 + 9 < TM || r0 + q * 10 < TM)
+            if ((q + 8) / 5 == kPart && (q * 10 + 9 < TM || r0 + q * 10 < TM))   // part 1: P q = 0..1, part 2: q = 2..6
                 cp_async16(sP + q * 10 * LDS_, gP + q * row_stride10);
+    }
+}
+__device__ __forceinline__ void load_stage(float *stage, const float *gA, const float *gP,
+                                           int64_t row_stride10, int r0) {
+    load_stage_part<0>(stage, gA, gP, row_stride10, r0);
+    load_stage_part<1>(stage, gA, gP, row_stride10, r0);
+    load_stage_part<2>(stage, gA, gP, row_stride10, r0);
+}
+
+// Exact argmax for the whole tile: lowest s in the winning chunk with
+// P[s] + A[j][s] == max.  8 lanes share one output (a float4 of the 32-wide chunk
+// each) so every load is a coalesced 128-byte row; kBatch outputs are in flight
+// per lane group (all shared-memory reads, then all global loads, then the
+// compares -- nothing in a batch waits on an earlier output's store).
+// bp_tile holds the winning chunk on entry and the source index on exit.
+template <bool kFullTile>
+__device__ __forceinline__ void rescan_tile(const float *best_tile, uint16_t *bp_tile,
+                                            const int *slot_frames, const float *P_rows,
+                                            const float *A_rows, int LDP, int cols_valid, int S, int t) {
+    constexpr int kBatch = 10;
+    constexpr int kRowsPerWarp = TM / (kThreads / kWarp);
+    const int lane = threadIdx.x % kWarp, warp = threadIdx.x / kWarp;
+    const int sub = lane >> 3, q4 = (lane & 7) * 4;
+    const float *Aq = A_rows + (int64_t)sub * LDP + q4;            // column `sub` of each group of 4
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int r = warp * kRowsPerWarp + rr;
+        if (t >= slot_frames[r]) continue;                          // warp-uniform
+        const float *Pq = P_rows + (int64_t)r * LDP + q4;
+        const float *best_row = best_tile + r * TN + sub;
+        uint16_t *bp_row = bp_tile + r * TN + sub;
+#pragma unroll 1
+        for (int cb = 0; cb < TN / 4; cb += kBatch) {
+            float best[kBatch];
+            int k0[kBatch];
+            float4 pv[kBatch], av[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                best[u] = best_row[(cb + u) * 4];
+                k0[u] = bp_row[(cb + u) * 4] * KC;
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const bool valid = kFullTile || (cb + u) * 4 + sub < cols_valid;
+                if (!valid) k0[u] = 0;                              // stale tile entry: stay in bounds
+                const int a_off = valid ? (cb + u) * 4 * LDP + k0[u] : 0;
+                pv[u] = __ldcg(reinterpret_cast<const float4 *>(Pq + k0[u]));
+                av[u] = __ldg(reinterpret_cast<const float4 *>(Aq + a_off));
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                unsigned key = 64;
+                if (pv[u].w + av[u].w == best[u]) key = q4 + 3;
+                if (pv[u].z + av[u].z == best[u]) key = q4 + 2;
+                if (pv[u].y + av[u].y == best[u]) key = q4 + 1;
+                if (pv[u].x + av[u].x == best[u]) key = q4;
+                // min over the 8 lanes of the output (xor 1, 2, 4 stays inside the group)
+                key = min(key, __shfl_xor_sync(kFullMask, key, 1));
+                key = min(key, __shfl_xor_sync(kFullMask, key, 2));
+                key = min(key, __shfl_xor_sync(kFullMask, key, 4));
+                // (key == 64 only for NaN input, outside the parity contract)
+                if ((lane & 7) == 0 && (kFullTile || (cb + u) * 4 + sub < cols_valid))
+                    bp_row[(cb + u) * 4] = (uint16_t)min(k0[u] + (int)key, S - 1);
+            }
+        }
     }
 }
 
@@ -170,9 +239,9 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             const int c_end = (jt == p.NJT - 1) ? LDP : min(j0 + TN, LDP);
             for (int r = warp; r < TM; r += kThreads / kWarp) {
                 const int item = slot_item[r];
-                float *dst0 = p.score[0] + (row0 + r) * LDP;
-                float *dst1 = p.score[1] + (row0 + r) * LDP;
-                float *dst2 = p.score[2] + (row0 + r) * LDP;
+                float *dst0 = p.score0 + (row0 + r) * LDP;
+                float *dst1 = dst0 + p.score_stride;
+                float *dst2 = dst1 + p.score_stride;
                 const float *obs = p.observation + (int64_t)max(item, 0) * p.T * S;
                 for (int c = j0 + lane; c < c_end; c += kWarp) {
                     if (item >= 0 && c < S) {
@@ -189,11 +258,14 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
         group_arrive(counter);
         group_wait(counter, barriers);
 
+        int buf = 0;                                    // buffer holding P_{t-1}
         for (int t = 1; t < batch_frames; ++t) {
             // three rotating buffers: a CTA that is already publishing step t+1 never
             // writes the buffer a slower CTA of the group still re-scans for step t
-            const float *P_cur = p.score[(t - 1) % 3];
-            float *P_new = p.score[t % 3];
+            const int buf_new = buf == 2 ? 0 : buf + 1;
+            const float *P_cur = p.score0 + buf * p.score_stride;
+            float *P_new = p.score0 + buf_new * p.score_stride;
+            buf = buf_new;
             const float *ld_P = P_cur + (row0 + ld_r0) * LDP + ld_c4 * 4;
 
             // emission tile for this step (raw; converted when consumed)
@@ -230,15 +302,20 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             for (int s = 0; s < nstages; ++s) {
                 cp_async_wait<1>();
                 __syncthreads();            // stage s landed; everyone is done with stage s-1
-                if (s + 2 < nstages)
-                    load_stage(ring + ((s + 2) % NSTAGE) * kStageFloats + ld_smem,
-                               ld_A + (s + 2) * KS, ld_P + (s + 2) * KS, ld_stride10, ld_r0);
-                cp_async_commit();
+                const bool refill = s + 2 < nstages;
+                float *refill_dst = ring + ((s + 2) % NSTAGE) * kStageFloats + ld_smem;
+                const float *refill_A = ld_A + (s + 2) * KS, *refill_P = ld_P + (s + 2) * KS;
 
                 const float *Ps = ring + (s % NSTAGE) * kStageFloats + r_base * LDS_;
                 const float *As = ring + (s % NSTAGE) * kStageFloats + (TM + c_base) * LDS_;
 #pragma unroll
                 for (int ch = 0; ch < KS / KC; ++ch) {
+                    if (refill) {
+                        if (ch == 0) load_stage_part<0>(refill_dst, refill_A, refill_P, ld_stride10, ld_r0);
+                        if (ch == 1) load_stage_part<1>(refill_dst, refill_A, refill_P, ld_stride10, ld_r0);
+                        if (ch == 2) load_stage_part<2>(refill_dst, refill_A, refill_P, ld_stride10, ld_r0);
+                    }
+                    if (ch == KS / KC - 1) cp_async_commit();
                     float acc[M][N];
 #pragma unroll
                     for (int k = 0; k < KC; k += 4) {
@@ -313,55 +390,12 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             // ---- exact argmax while the rest of the group catches up: lowest s in the
             //      winning chunk with P[s] + A[j][s] == max.  8 lanes share one output
             //      (a float4 of the chunk each), so every load is a coalesced 128-byte row.
-            {
-                constexpr int kBatch = 10;                        // outputs in flight per lane group
-                const int sub = lane >> 3, q4 = (lane & 7) * 4;
-                for (int rr = 0; rr < TM / (kThreads / kWarp); ++rr) {
-                    const int r = warp * (TM / (kThreads / kWarp)) + rr;
-                    if (t >= slot_frames[r]) continue;            // warp-uniform
-                    const float *Prow = P_cur + (row0 + r) * LDP + q4;
-                    const float *Arow = p.transition + (int64_t)j0 * LDP + q4;
-#pragma unroll 1
-                    for (int cb = 0; cb < TN / 4; cb += kBatch) {
-                        float best[kBatch];
-                        int k0[kBatch];
-                        float4 pv[kBatch], av[kBatch];
-                        // all shared-memory reads, then all global loads, then the compares:
-                        // nothing in a batch waits on an earlier output's store
-#pragma unroll
-                        for (int u = 0; u < kBatch; ++u) {
-                            const int col = (cb + u) * 4 + sub;
-                            best[u] = best_tile[r * TN + col];
-                            k0[u] = bp_tile[r * TN + col] * KC;
-                        }
-#pragma unroll
-                        for (int u = 0; u < kBatch; ++u) {
-                            const int col = (cb + u) * 4 + sub;
-                            const bool valid = j0 + col < S;
-                            if (!valid) k0[u] = 0;                // stale tile entry: stay in bounds
-                            pv[u] = __ldcg(reinterpret_cast<const float4 *>(Prow + k0[u]));
-                            av[u] = __ldg(reinterpret_cast<const float4 *>(
-                                Arow + (int64_t)(valid ? col : 0) * LDP + k0[u]));
-                        }
-#pragma unroll
-                        for (int u = 0; u < kBatch; ++u) {
-                            const int col = (cb + u) * 4 + sub;
-                            unsigned key = 64;
-                            if (pv[u].w + av[u].w == best[u]) key = q4 + 3;
-                            if (pv[u].z + av[u].z == best[u]) key = q4 + 2;
-                            if (pv[u].y + av[u].y == best[u]) key = q4 + 1;
-                            if (pv[u].x + av[u].x == best[u]) key = q4;
-                            // min over the 8 lanes of the output (xor 1,2,4 stays inside the group)
-                            key = min(key, __shfl_xor_sync(kFullMask, key, 1));
-                            key = min(key, __shfl_xor_sync(kFullMask, key, 2));
-                            key = min(key, __shfl_xor_sync(kFullMask, key, 4));
-                            // (key == 64 only for NaN input, outside the parity contract)
-                            if ((lane & 7) == 0 && j0 + col < S)
-                                bp_tile[r * TN + col] = (uint16_t)min(k0[u] + (int)key, S - 1);
-                        }
-                    }
-                }
-            }
+            if (j0 + TN <= S)
+                rescan_tile<true>(best_tile, bp_tile, slot_frames, P_cur + row0 * LDP, p.transition + (int64_t)j0 * LDP,
+                                  LDP, S - j0, S, t);
+            else
+                rescan_tile<false>(best_tile, bp_tile, slot_frames, P_cur + row0 * LDP, p.transition + (int64_t)j0 * LDP,
+                                   LDP, S - j0, S, t);
             __syncthreads();
 
             // ---- backpointers: coalesced, vectorised uint16 stores ----
@@ -383,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
         }
 
         // ---- final scores out (viterbi.cpp:111-113) + first-occurrence argmax (:218) ----
-        const float *P_fin = p.score[(batch_frames - 1) % 3];
+        const float *P_fin = p.score0 + buf * p.score_stride;
         for (int r = jt * (kThreads / kWarp) + warp; r < TM; r += p.NJT * (kThreads / kWarp)) {
             const int item = slot_item[r];
             if (item < 0) continue;
@@ -437,9 +471,8 @@ static cudaError_t launch_tiled_t(const ForwardArgs &a, cudaStream_t stream) {
     p.initial = a.initial;
     p.frames = a.ws.frames;
     p.order = a.ws.order;
-    p.score[0] = a.ws.score[0];
-    p.score[1] = a.ws.score[1];
-    p.score[2] = a.ws.score[2];
+    p.score0 = a.ws.score[0];
+    p.score_stride = a.ws.score[1] - a.ws.score[0];
     p.backptr = a.ws.backptr;
     p.posterior = a.posterior;
     p.final_state = a.ws.final_state;
