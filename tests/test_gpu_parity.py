@@ -195,6 +195,24 @@ def test_host_entry_matches_device_entry(oracle):
     assert np.array_equal(bits(post.numpy()), bits(want_post))
 
 
+def test_host_entry_streams_large_pinned_batches():
+    """Pinned batches >= 64 MB are copied in along T on a second stream while the
+    forward kernel runs (it polls a frames-ready word); results must not change."""
+    rng = np.random.default_rng(31)
+    B, T, S = 20, 700, 1440                                   # 80 MB
+    obs = torch.from_numpy(cases.log_softmax(rng.standard_normal((B, T, S)))).pin_memory()
+    frames = torch.from_numpy(rng.integers(1, T + 1, size=B).astype(np.int32))
+    frames[3] = T
+    A = torch.from_numpy(cases.log_triangular_transition(S))
+    init = torch.from_numpy(cases.log_softmax(rng.standard_normal((S,))))
+    want = torbi_b200.decode(obs.cuda(), frames, A.cuda(), init.cuda()).cpu()
+    for _ in range(2):
+        got = torbi_b200.decode_host(obs, frames, A, init, gpu=0)
+        assert torch.equal(got, want)
+    pageable = torbi_b200.decode_host(obs.clone(), frames, A, init, gpu=0)   # not pinned: copied up front
+    assert torch.equal(pageable, want)
+
+
 def test_multi_gpu_list_api(oracle):
     obs, frames, A, init = random_problem(22, 10, 20, 128)
     want = oracle.c_decode(obs, frames, A, init)

@@ -134,10 +134,18 @@ size_t torbi_b200_workspace_bytes(int64_t B, int64_t T, int64_t S, uint32_t) {
     return carve_workspace(nullptr, B, T, S).bytes;
 }
 
-int torbi_b200_decode(const float *observation, const int32_t *batch_frames,
-                      const float *transition, const float *initial, int64_t B, int64_t T,
-                      int64_t S, uint32_t flags, int32_t *indices, float *posterior,
-                      void *workspace, size_t workspace_bytes, void *stream_) {
+}  // extern "C"
+
+namespace {
+
+// torbi_b200_decode plus `frames_ready`: a device word the forward kernel polls
+// when the observations are still being copied in (host entry); nullptr otherwise.
+// `*streamed` reports whether the chosen kernel honours it.
+int decode_device(const float *observation, const int32_t *batch_frames,
+                  const float *transition, const float *initial, int64_t B, int64_t T,
+                  int64_t S, uint32_t flags, int32_t *indices, float *posterior,
+                  void *workspace, size_t workspace_bytes, void *stream_,
+                  const int32_t *frames_ready, bool *streamed) {
     g_error[0] = 0;
     int rc = validate_shape(B, T, S);
     if (rc) return rc;
@@ -189,6 +197,7 @@ int torbi_b200_decode(const float *observation, const int32_t *batch_frames,
     a.flags = flags;
     a.sm_count = info.sm_count;
     a.ws = ws;
+    a.frames_ready = frames_ready;
 
     const bool timed = flags & TORBI_B200_TIME_KERNELS;
     g_timing.valid = false;
@@ -201,10 +210,13 @@ int torbi_b200_decode(const float *observation, const int32_t *batch_frames,
     bool tiled = forward_tiled_supported(a) && !(flags & TORBI_B200_FORCE_GENERIC);
     if ((flags & TORBI_B200_FORCE_TILED) && !tiled)
         return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "tiled kernel does not support this shape");
+    if (streamed) *streamed = tiled;
     if (tiled) {
         e = launch_forward_tiled(a, stream);
         g_last_kernel = "forward_tiled";
     } else {
+        if (frames_ready)
+            return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "internal: generic kernel cannot stream");
         e = launch_forward_generic(a, stream);
         g_last_kernel = "forward_generic";
     }
@@ -216,8 +228,20 @@ int torbi_b200_decode(const float *observation, const int32_t *batch_frames,
         cudaEventRecord(g_timing.ev[2], stream);
         g_timing.valid = true;
     }
-    g_launches += 2;
+    g_launches += tiled ? 3 : 2;      // (pad_transition +) forward + backtrace
     return TORBI_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int torbi_b200_decode(const float *observation, const int32_t *batch_frames,
+                      const float *transition, const float *initial, int64_t B, int64_t T,
+                      int64_t S, uint32_t flags, int32_t *indices, float *posterior,
+                      void *workspace, size_t workspace_bytes, void *stream) {
+    return decode_device(observation, batch_frames, transition, initial, B, T, S, flags, indices,
+                         posterior, workspace, workspace_bytes, stream, nullptr, nullptr);
 }
 
 int torbi_b200_last_timing(float *forward_ms, float *backtrace_ms) {
@@ -241,10 +265,15 @@ int torbi_b200_last_timing(float *forward_ms, float *backtrace_ms) {
 // ---------------------------------------------------------------------------
 namespace {
 
+constexpr int kMaxChunks = 16;
+
 struct Arena {
     void *base = nullptr;
     size_t bytes = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // kernels, small copies, results
+    cudaStream_t copy_stream = nullptr;  // observation chunks streamed in under the kernel
+    cudaEvent_t reset_event = nullptr;
+    int32_t *ready_host = nullptr;       // pinned: frames available after each chunk
     std::mutex busy;  // one decode at a time per device arena
 };
 
@@ -287,12 +316,17 @@ int decode_items_on_device(const float *observation, const int32_t *batch_frames
     const size_t idx_bytes = align_up(sizeof(int32_t) * count * T, 256);
     const size_t post_bytes = posterior ? align_up(sizeof(float) * count * S, 256) : 0;
     const size_t ws_bytes = carve_workspace(nullptr, count, T, S).bytes;
-    const size_t total = obs_bytes + tr_bytes + init_bytes + idx_bytes + post_bytes + ws_bytes;
+    const size_t total = obs_bytes + tr_bytes + init_bytes + idx_bytes + post_bytes + ws_bytes + 256;
 
     cudaError_t e;
     if (!arena->stream) {
         e = cudaStreamCreateWithFlags(&arena->stream, cudaStreamNonBlocking);
-        if (e != cudaSuccess) return fail_cuda(e, "cudaStreamCreate");
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&arena->copy_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&arena->reset_event, cudaEventDisableTiming);
+        if (e == cudaSuccess)
+            e = cudaHostAlloc(reinterpret_cast<void **>(&arena->ready_host),
+                              sizeof(int32_t) * kMaxChunks, cudaHostAllocDefault);
+        if (e != cudaSuccess) return fail_cuda(e, "create streams");
     }
     if (arena->bytes < total) {
         if (arena->base) cudaFree(arena->base);
@@ -312,26 +346,59 @@ int decode_items_on_device(const float *observation, const int32_t *batch_frames
     float *d_init = reinterpret_cast<float *>(p); p += init_bytes;
     int32_t *d_idx = reinterpret_cast<int32_t *>(p); p += idx_bytes;
     float *d_post = posterior ? reinterpret_cast<float *>(p) : nullptr; p += post_bytes;
-    void *d_ws = p;
+    void *d_ws = p; p += ws_bytes;
+    int32_t *d_ready = reinterpret_cast<int32_t *>(p);
     cudaStream_t stream = arena->stream;
 
     e = cudaMemcpyAsync(d_tr, transition, sizeof(float) * S * S, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(d_init, initial, sizeof(float) * S, cudaMemcpyHostToDevice, stream);
-    // items that are consecutive in the caller's batch travel in one copy
     std::vector<int32_t> frames(count);
-    for (int64_t i = 0; i < count && e == cudaSuccess;) {
-        int64_t run = 1;
-        while (i + run < count && items[i + run] == items[i] + run) ++run;
-        e = cudaMemcpyAsync(d_obs + i * T * S, observation + (int64_t)items[i] * T * S,
-                            sizeof(float) * run * T * S, cudaMemcpyHostToDevice, stream);
-        i += run;
-    }
-    if (e != cudaSuccess) return fail_cuda(e, "host->device copy");
     for (int64_t i = 0; i < count; ++i) frames[i] = batch_frames[items[i]];
 
-    rc = torbi_b200_decode(d_obs, frames.data(), d_tr, d_init, count, T, S, flags, d_idx, d_post,
-                           d_ws, ws_bytes, stream);
+    // Large pinned batches are streamed in along T on a second stream while the
+    // forward kernel already runs: step t only needs frame t (the kernel polls
+    // `d_ready`).  Small, pageable or generic-kernel batches are copied up front.
+    const size_t row_bytes = sizeof(float) * T * S;
+    cudaPointerAttributes attr{};
+    const bool pinned = cudaPointerGetAttributes(&attr, observation) == cudaSuccess &&
+                        attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const bool can_tile = padded_dests(S) / kTileDests <= info.sm_count && !(flags & TORBI_B200_FORCE_GENERIC);
+    const bool stream_in = pinned && can_tile && T >= 64 && row_bytes < (size_t(1) << 31) &&
+                           (size_t)count * row_bytes >= (size_t(64) << 20);
+    const int chunks = stream_in ? (int)std::min<int64_t>(16, std::max<int64_t>(2, T / 64)) : 1;
+    if (stream_in) {
+        e = cudaMemsetAsync(d_ready, 0, sizeof(int32_t), arena->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(arena->reset_event, arena->copy_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, arena->reset_event, 0);
+    }
+    for (int c = 0; c < chunks && e == cudaSuccess; ++c) {
+        const int64_t t0 = T * c / chunks, t1 = T * (c + 1) / chunks;
+        // items that are consecutive in the caller's batch travel in one copy
+        for (int64_t i = 0; i < count && e == cudaSuccess;) {
+            int64_t run = 1;
+            while (i + run < count && items[i + run] == items[i] + run) ++run;
+            const float *src = observation + (int64_t)items[i] * T * S + t0 * S;
+            float *dst = d_obs + i * T * S + t0 * S;
+            if (chunks == 1)
+                e = cudaMemcpyAsync(dst, src, row_bytes * run, cudaMemcpyHostToDevice, stream);
+            else
+                e = cudaMemcpy2DAsync(dst, row_bytes, src, row_bytes, sizeof(float) * (t1 - t0) * S,
+                                      run, cudaMemcpyHostToDevice, arena->copy_stream);
+            i += run;
+        }
+        if (stream_in && e == cudaSuccess) {
+            arena->ready_host[c] = (int32_t)t1;
+            e = cudaMemcpyAsync(d_ready, &arena->ready_host[c], sizeof(int32_t),
+                                cudaMemcpyHostToDevice, arena->copy_stream);
+        }
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "host->device copy");
+
+    bool streamed = false;
+    rc = decode_device(d_obs, frames.data(), d_tr, d_init, count, T, S, flags, d_idx, d_post, d_ws,
+                       ws_bytes, stream, stream_in ? d_ready : nullptr, &streamed);
     if (rc) return rc;
 
     for (int64_t i = 0; i < count && e == cudaSuccess;) {
@@ -345,6 +412,7 @@ int decode_items_on_device(const float *observation, const int32_t *batch_frames
         i += run;
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess && stream_in) e = cudaStreamSynchronize(arena->copy_stream);
     if (e != cudaSuccess) return fail_cuda(e, "device->host copy / synchronize");
     return TORBI_B200_OK;
 }
@@ -431,9 +499,15 @@ void torbi_b200_release(void) {
         DeviceGuard guard(kv.first);
         if (a->base) cudaFree(a->base);
         if (a->stream) cudaStreamDestroy(a->stream);
+        if (a->copy_stream) cudaStreamDestroy(a->copy_stream);
+        if (a->reset_event) cudaEventDestroy(a->reset_event);
+        if (a->ready_host) cudaFreeHost(a->ready_host);
         a->base = nullptr;
         a->bytes = 0;
         a->stream = nullptr;
+        a->copy_stream = nullptr;
+        a->reset_event = nullptr;
+        a->ready_host = nullptr;
     }
 }
 

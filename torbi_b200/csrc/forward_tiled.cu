@@ -69,6 +69,11 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(kPending));
 }
 
+__device__ __forceinline__ int ld_acquire_sys(const int32_t *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -103,6 +108,7 @@ struct TiledParams {
     float *posterior;           // (B,S) or null
     int32_t *final_state;       // (B,)
     unsigned *sync;             // one counter per group
+    const int32_t *frames_ready;  // frames of `observation` copied in so far, or null
     int64_t T;
     int S, LDP, NJT, NG, num_batches;
 };
@@ -201,6 +207,22 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
     uint16_t *bp_tile = reinterpret_cast<uint16_t *>(best_tile + TM * TN);  // [TM][TN] chunk, then index
     int *slot_item = reinterpret_cast<int *>(bp_tile + TM * TN);       // [TM]
     int *slot_frames = slot_item + TM;                                 // [TM]
+    __shared__ int ready_shared;
+    int ready = p.frames_ready ? 0 : 0x7fffffff;    // frames of `observation` known to be in HBM
+    // the host entry copies the batch in T-chunks while this kernel runs: block
+    // until frame `t` has landed (one poll per chunk, not per step)
+    auto wait_for_frame = [&](int t) {
+        if (t >= ready) {
+            if (threadIdx.x == 0) {
+                int r;
+                while ((r = ld_acquire_sys(p.frames_ready)) <= t) __nanosleep(200);
+                ready_shared = r;
+            }
+            __syncthreads();
+            ready = ready_shared;
+            __syncthreads();
+        }
+    };
 
     const int group = blockIdx.x / p.NJT, jt = blockIdx.x % p.NJT;
     if (group >= p.NG) return;
@@ -235,6 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
         const int batch_frames = slot_frames[0];        // longest first
 
         // ---- t = 0: P_0[s] = obs[0][s] + initial[s]   (viterbi.cpp:72-76) ----
+        wait_for_frame(0);
         {
             const int c_end = (jt == p.NJT - 1) ? LDP : min(j0 + TN, LDP);
             for (int r = warp; r < TM; r += kThreads / kWarp) {
@@ -269,6 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             const float *ld_P = P_cur + (row0 + ld_r0) * LDP + ld_c4 * 4;
 
             // emission tile for this step (raw; converted when consumed)
+            wait_for_frame(t);
             if (obs_vec) {
                 for (int idx = tid; idx < TM * (TN / 4); idx += kThreads) {
                     const int r = idx / (TN / 4), c4 = idx % (TN / 4);
@@ -477,6 +501,7 @@ static cudaError_t launch_tiled_t(const ForwardArgs &a, cudaStream_t stream) {
     p.posterior = a.posterior;
     p.final_state = a.ws.final_state;
     p.sync = a.ws.sync;
+    p.frames_ready = a.frames_ready;
     p.T = a.T;
     p.S = (int)a.S;
     p.LDP = (int)tiled_ldp(a.S);

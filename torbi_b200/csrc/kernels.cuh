@@ -10,6 +10,9 @@ struct ForwardArgs {
     const float *transition;   // device (S,S) [dest][src]
     const float *initial;      // device (S,)
     float *posterior;          // device (B,S) or nullptr
+    // device word holding how many leading frames of `observation` are valid so far
+    // (the host entry streams the batch in while the recursion runs); nullptr = all
+    const int32_t *frames_ready;
     int64_t B, T, S;
     int64_t max_frames;        // max(batch_frames)
     uint32_t flags;
