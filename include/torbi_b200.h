@@ -58,6 +58,11 @@ extern "C" {
 /* record CUDA events around the forward and backtrace kernels on the caller's
  * stream so torbi_b200_last_timing can report their device time */
 #define TORBI_B200_TIME_KERNELS (1u << 10)
+/* force the batch height of the tiled kernel (tests / tuning): bits 12-13 = 1, 2, 3 for 16, 32, 64 rows */
+#define TORBI_B200_TILE_ROWS_MASK (3u << 12)
+#define TORBI_B200_TILE_ROWS_16 (1u << 12)
+#define TORBI_B200_TILE_ROWS_32 (2u << 12)
+#define TORBI_B200_TILE_ROWS_64 (3u << 12)
 
 TORBI_B200_API int torbi_b200_abi_version(void);
 

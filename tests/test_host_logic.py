@@ -32,6 +32,9 @@ def test_flag_values_match_header():
     for name in ('OBS_IS_PROBABILITY', 'EPS_FLOOR', 'FORCE_GENERIC', 'FORCE_TILED', 'TIME_KERNELS'):
         shift = int(re.search(rf'#define TORBI_B200_{name} \(1u << (\d+)\)', header).group(1))
         assert getattr(_ffi, name) == 1 << shift
+    for name, value in (('TILE_ROWS_16', 1), ('TILE_ROWS_32', 2), ('TILE_ROWS_64', 3)):
+        assert re.search(rf'#define TORBI_B200_{name} \({value}u << 12\)', header)
+        assert getattr(_ffi, name) == value << 12
     for name in ('INVALID_ARGUMENT', 'WORKSPACE', 'CUDA', 'OUT_OF_MEMORY'):
         code = int(re.search(rf'#define TORBI_B200_ERR_{name} \((-\d+)\)', header).group(1))
         assert getattr(_ffi, f'ERR_{name}') == code

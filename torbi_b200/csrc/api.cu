@@ -198,6 +198,12 @@ int decode_device(const float *observation, const int32_t *batch_frames,
     a.sm_count = info.sm_count;
     a.ws = ws;
     a.frames_ready = frames_ready;
+    {
+        std::vector<int32_t> sorted(B);
+        for (int64_t i = 0; i < B; ++i) sorted[i] = batch_frames[order[i]];
+        a.tile_rows = tiled_choose_rows(sorted.data(), B, S, info.sm_count);
+        if (flags & TORBI_B200_TILE_ROWS_MASK) a.tile_rows = 16 << (((flags & TORBI_B200_TILE_ROWS_MASK) >> 12) - 1);
+    }
 
     const bool timed = flags & TORBI_B200_TIME_KERNELS;
     g_timing.valid = false;

@@ -20,7 +20,8 @@
 // records the FIRST chunk attaining the final maximum, then that chunk is
 // re-scanned for the lowest s with P[s] + A[j][s] == max.  This reproduces the
 // reference's ascending strict-`>` scan (viterbi.cpp:94-101) bit for bit.
-#include <cooperative_groups.h>
+#include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -29,22 +30,26 @@ namespace torbi_b200 {
 
 namespace {
 
-constexpr int TM = 64;          // sequences per batch (rows of the tile)
 constexpr int TN = kTileDests;  // destination states per CTA (columns of the tile)
 constexpr int KC = 32;          // source states per argmax chunk
 constexpr int KS = kStageSources;  // source states per pipeline stage (3 chunks)
 constexpr int LDS_ = KS + 4;    // smem row stride in floats: rows 4 banks apart
 constexpr int NSTAGE = 3;
 constexpr int kThreads = 256;
-constexpr int M = 4, N = 5;     // register tile: 4 sequences x 5 destination states
-constexpr int LANES_B = 8, LANES_J = 4, WARPS_J = 4;
+constexpr int N = 5;            // register tile: M sequences x 5 destination states
+constexpr int LANES_B = 8, LANES_J = 4, WARPS_J = 4, WARPS_B = 2;
 
-constexpr int kStageFloats = (TM + TN) * LDS_;
-constexpr size_t kSmemBytes =
-    sizeof(float) * (NSTAGE * kStageFloats + 2 * TM * TN)  // ring + emission/score tile + max tile
-    + sizeof(uint16_t) * TM * TN                           // winning chunk -> backpointer tile
-    + sizeof(int) * 2 * TM;                                // per-slot item id and length
-static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+// The batch tile height is a template parameter: M = 4, 2, 1 rows per thread
+// give TM = 64, 32, 16 sequences per batch (smaller tiles fill the machine when
+// the batch is small or ragged, at a lower math/LDS ratio).
+constexpr int tile_rows(int M) { return WARPS_B * LANES_B * M; }
+constexpr int stage_floats(int M) { return (tile_rows(M) + TN) * LDS_; }
+constexpr size_t smem_bytes(int M) {
+    return sizeof(float) * (NSTAGE * stage_floats(M) + 2 * tile_rows(M) * TN)  // ring + emission/score + max tiles
+           + sizeof(uint16_t) * tile_rows(M) * TN                              // winning chunk -> backpointer tile
+           + sizeof(int) * 2 * tile_rows(M);                                   // per-slot item id and length
+}
+static_assert(smem_bytes(4) <= 227 * 1024, "shared memory budget");
 constexpr int kLoaders = 240;                 // 24 float4 columns x 10 rows per pass
 static_assert(KS / 4 == 24 && TN % 10 == 0, "loader mapping");
 
@@ -107,7 +112,7 @@ struct TiledParams {
     uint16_t *backptr;          // (B,T,S)
     float *posterior;           // (B,S) or null
     int32_t *final_state;       // (B,)
-    unsigned *sync;             // one counter per group
+    unsigned *sync;             // per group: barrier counter (+0) and current batch (+1); queue head at [0] of the last line
     const int32_t *frames_ready;  // frames of `observation` copied in so far, or null
     int64_t T;
     int S, LDP, NJT, NG, num_batches;
@@ -118,7 +123,7 @@ struct TiledParams {
 // so every address is a fixed per-thread base plus a constant stride.  The 15
 // copies are issued in three parts, one per argmax chunk, so they interleave
 // with the math instead of piling up in the load/store queue.
-template <int kPart>
+template <int TM, int kPart>
 __device__ __forceinline__ void load_stage_part(float *stage, const float *gA, const float *gP,
                                                 int64_t row_stride10, int r0) {
     if (threadIdx.x < kLoaders) {
@@ -133,11 +138,12 @@ __device__ __forceinline__ void load_stage_part(float *stage, const float *gA, c
                 cp_async16(sP + q * 10 * LDS_, gP + q * row_stride10);
     }
 }
+template <int TM>
 __device__ __forceinline__ void load_stage(float *stage, const float *gA, const float *gP,
                                            int64_t row_stride10, int r0) {
-    load_stage_part<0>(stage, gA, gP, row_stride10, r0);
-    load_stage_part<1>(stage, gA, gP, row_stride10, r0);
-    load_stage_part<2>(stage, gA, gP, row_stride10, r0);
+    load_stage_part<TM, 0>(stage, gA, gP, row_stride10, r0);
+    load_stage_part<TM, 1>(stage, gA, gP, row_stride10, r0);
+    load_stage_part<TM, 2>(stage, gA, gP, row_stride10, r0);
 }
 
 // Exact argmax for the whole tile: lowest s in the winning chunk with
@@ -146,7 +152,7 @@ __device__ __forceinline__ void load_stage(float *stage, const float *gA, const 
 // per lane group (all shared-memory reads, then all global loads, then the
 // compares -- nothing in a batch waits on an earlier output's store).
 // bp_tile holds the winning chunk on entry and the source index on exit.
-template <bool kFullTile>
+template <int TM, bool kFullTile>
 __device__ __forceinline__ void rescan_tile(const float *best_tile, uint16_t *bp_tile,
                                             const int *slot_frames, const float *P_rows,
                                             const float *A_rows, int LDP, int cols_valid, int S, int t) {
@@ -198,8 +204,10 @@ __device__ __forceinline__ void rescan_tile(const float *best_tile, uint16_t *bp
     }
 }
 
-template <uint32_t kFlags>
+template <int M, uint32_t kFlags>
 __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledParams p) {
+    constexpr int TM = tile_rows(M);
+    constexpr int kStageFloats = stage_floats(M);
     extern __shared__ __align__(16) float smem[];
     float *ring = smem;
     float *tile = smem + NSTAGE * kStageFloats;                      // [TM][TN] emission -> new score
@@ -245,7 +253,16 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
     const float *ld_A = p.transition + (int64_t)(j0 + ld_r0) * LDP + ld_c4 * 4;
     const int64_t ld_stride10 = (int64_t)10 * LDP;
 
-    for (int batch = group; batch < p.num_batches; batch += p.NG) {
+    unsigned *queue_head = p.sync + p.NG * 32;       // batches are handed out longest first
+    for (;;) {
+        // the group's first CTA takes the next batch off the queue; the group
+        // barrier publishes it to the others (dynamic LPT over groups)
+        if (jt == 0 && tid == 0) counter[1] = atomicAdd(queue_head, 1u);
+        barriers += p.NJT;
+        group_arrive(counter);
+        group_wait(counter, barriers);
+        const int batch = (int)__ldcg(counter + 1);
+        if (batch >= p.num_batches) break;
         const int64_t row0 = (int64_t)batch * TM;
         __syncthreads();
         if (tid < TM) {
@@ -310,10 +327,10 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                 }
             }
             // prologue: stages 0 and 1
-            load_stage(ring + ld_smem, ld_A, ld_P, ld_stride10, ld_r0);
+            load_stage<TM>(ring + ld_smem, ld_A, ld_P, ld_stride10, ld_r0);
             cp_async_commit();
             if (nstages > 1)
-                load_stage(ring + kStageFloats + ld_smem, ld_A + KS, ld_P + KS, ld_stride10, ld_r0);
+                load_stage<TM>(ring + kStageFloats + ld_smem, ld_A + KS, ld_P + KS, ld_stride10, ld_r0);
             cp_async_commit();
 
             float cur[M][N];
@@ -335,9 +352,9 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
 #pragma unroll
                 for (int ch = 0; ch < KS / KC; ++ch) {
                     if (refill) {
-                        if (ch == 0) load_stage_part<0>(refill_dst, refill_A, refill_P, ld_stride10, ld_r0);
-                        if (ch == 1) load_stage_part<1>(refill_dst, refill_A, refill_P, ld_stride10, ld_r0);
-                        if (ch == 2) load_stage_part<2>(refill_dst, refill_A, refill_P, ld_stride10, ld_r0);
+                        if (ch == 0) load_stage_part<TM, 0>(refill_dst, refill_A, refill_P, ld_stride10, ld_r0);
+                        if (ch == 1) load_stage_part<TM, 1>(refill_dst, refill_A, refill_P, ld_stride10, ld_r0);
+                        if (ch == 2) load_stage_part<TM, 2>(refill_dst, refill_A, refill_P, ld_stride10, ld_r0);
                     }
                     if (ch == KS / KC - 1) cp_async_commit();
                     float acc[M][N];
@@ -415,10 +432,10 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             //      winning chunk with P[s] + A[j][s] == max.  8 lanes share one output
             //      (a float4 of the chunk each), so every load is a coalesced 128-byte row.
             if (j0 + TN <= S)
-                rescan_tile<true>(best_tile, bp_tile, slot_frames, P_cur + row0 * LDP, p.transition + (int64_t)j0 * LDP,
+                rescan_tile<TM, true>(best_tile, bp_tile, slot_frames, P_cur + row0 * LDP, p.transition + (int64_t)j0 * LDP,
                                   LDP, S - j0, S, t);
             else
-                rescan_tile<false>(best_tile, bp_tile, slot_frames, P_cur + row0 * LDP, p.transition + (int64_t)j0 * LDP,
+                rescan_tile<TM, false>(best_tile, bp_tile, slot_frames, P_cur + row0 * LDP, p.transition + (int64_t)j0 * LDP,
                                    LDP, S - j0, S, t);
             __syncthreads();
 
@@ -487,8 +504,9 @@ bool forward_tiled_supported(const ForwardArgs &a) {
     return njt <= a.sm_count && a.ws.transition_pad != nullptr;
 }
 
-template <uint32_t kFlags>
+template <int M, uint32_t kFlags>
 static cudaError_t launch_tiled_t(const ForwardArgs &a, cudaStream_t stream) {
+    constexpr int TM = tile_rows(M);
     TiledParams p{};
     p.observation = a.observation;
     p.transition = a.ws.transition_pad;
@@ -509,29 +527,63 @@ static cudaError_t launch_tiled_t(const ForwardArgs &a, cudaStream_t stream) {
     p.NJT = SJ / TN;
     p.num_batches = (int)((a.B + TM - 1) / TM);
     p.NG = std::min(a.sm_count / p.NJT, p.num_batches);
-    if (p.NG * 32 > (int)kSyncWords) return cudaErrorInvalidValue;
+    if ((p.NG + 1) * 32 > (int)kSyncWords) return cudaErrorInvalidValue;
 
     pad_transition_kernel<<<a.sm_count * 4, 256, 0, stream>>>(a.transition, a.ws.transition_pad,
                                                               p.S, SJ, p.LDP);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
 
-    auto kernel = forward_tiled_kernel<kFlags>;
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    auto kernel = forward_tiled_kernel<M, kFlags>;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(M));
     if (e != cudaSuccess) return e;
     void *args[] = {(void *)&p};
     // cooperative launch: all CTAs of a group must be co-resident for the
     // per-step counter barrier; the launch fails instead of deadlocking
     return cudaLaunchCooperativeKernel((void *)kernel, dim3(p.NG * p.NJT), dim3(kThreads), args,
-                                       kSmemBytes, stream);
+                                       smem_bytes(M), stream);
+}
+
+template <int M>
+static cudaError_t launch_tiled_m(const ForwardArgs &a, cudaStream_t stream) {
+    switch (a.flags & 3u) {
+        case 0: return launch_tiled_t<M, 0>(a, stream);
+        case 1: return launch_tiled_t<M, 1>(a, stream);
+        case 2: return launch_tiled_t<M, 2>(a, stream);
+        default: return launch_tiled_t<M, 3>(a, stream);
+    }
+}
+
+// Relative cost of one timestep of a TM-row batch (measured on the B200, S = 1440).
+static double step_cost(int tm) { return tm == 64 ? 1.0 : tm == 32 ? 0.60 : 0.51; }
+
+// Batch height for this call: simulate longest-first list scheduling of the
+// length-sorted batches over the CTA groups for TM = 64 / 32 / 16 and take the
+// smallest makespan.  `frames_sorted` is descending.
+int tiled_choose_rows(const int32_t *frames_sorted, int64_t B, int64_t S, int sm_count) {
+    const int njt = (int)(tiled_sj(S) / TN);
+    const int groups_max = std::max(1, sm_count / njt);
+    int best_tm = 64;
+    double best = 1e300;
+    for (int tm : {64, 32, 16}) {
+        const int batches = (int)((B + tm - 1) / tm);
+        const int groups = std::min(groups_max, batches);
+        std::vector<double> load(groups, 0.0);
+        for (int b = 0; b < batches; ++b) {     // batches arrive longest first: greedy = LPT
+            auto it = std::min_element(load.begin(), load.end());
+            *it += frames_sorted[(int64_t)b * tm] * step_cost(tm);
+        }
+        const double makespan = *std::max_element(load.begin(), load.end());
+        if (makespan < best * 0.97) { best = makespan; best_tm = tm; }   // prefer the taller tile on near-ties
+    }
+    return best_tm;
 }
 
 cudaError_t launch_forward_tiled(const ForwardArgs &a, cudaStream_t stream) {
-    switch (a.flags & 3u) {
-        case 0: return launch_tiled_t<0>(a, stream);
-        case 1: return launch_tiled_t<1>(a, stream);
-        case 2: return launch_tiled_t<2>(a, stream);
-        default: return launch_tiled_t<3>(a, stream);
+    switch (a.tile_rows) {
+        case 16: return launch_tiled_m<1>(a, stream);
+        case 32: return launch_tiled_m<2>(a, stream);
+        default: return launch_tiled_m<4>(a, stream);
     }
 }
 

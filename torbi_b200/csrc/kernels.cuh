@@ -17,6 +17,7 @@ struct ForwardArgs {
     int64_t max_frames;        // max(batch_frames)
     uint32_t flags;
     int sm_count;
+    int tile_rows;             // batch height of the tiled kernel: 64, 32 or 16
     Workspace ws;
 };
 
@@ -26,6 +27,7 @@ cudaError_t launch_forward_generic(const ForwardArgs &a, cudaStream_t stream);
 // forward_tiled.cu -- batch-tiled max-plus "GEMM" per timestep, persistent grid
 bool forward_tiled_supported(const ForwardArgs &a);
 cudaError_t launch_forward_tiled(const ForwardArgs &a, cudaStream_t stream);
+int tiled_choose_rows(const int32_t *frames_sorted, int64_t B, int64_t S, int sm_count);
 
 // backtrace.cu -- ragged backtrace + tail fill (viterbi.cpp:140-160, :219-221)
 cudaError_t launch_backtrace(const Workspace &ws, int32_t *indices, int64_t B, int64_t T,
