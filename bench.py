@@ -51,7 +51,7 @@ def parse_args():
     parser.add_argument('--states', type=int, default=1440)
     parser.add_argument('--no-e2e', action='store_true')
     parser.add_argument('--no-cpu-baseline', action='store_true')
-    parser.add_argument('--kernel', default='auto', choices=['auto', 'generic', 'tiled'])
+    parser.add_argument('--kernel', default='auto', choices=['auto', 'generic', 'tiled', 'wide'])
     parser.add_argument('--tile-rows', type=int, default=0, choices=[0, 16, 32, 64])
     return parser.parse_args()
 
@@ -262,7 +262,7 @@ def bench_graft(args):
     B, T, S = args.batch, args.frames, args.states
     obs, frames, A, init = make_workload(args, device, 1234 + rank)
     flags = _ffi.EPS_FLOOR | _ffi.TIME_KERNELS
-    flags |= {'auto': 0, 'generic': _ffi.FORCE_GENERIC, 'tiled': _ffi.FORCE_TILED}[args.kernel]
+    flags |= {'auto': 0, 'generic': _ffi.FORCE_GENERIC, 'tiled': _ffi.FORCE_TILED, 'wide': _ffi.FORCE_WIDE}[args.kernel]
     flags |= {0: 0, 16: _ffi.TILE_ROWS_16, 32: _ffi.TILE_ROWS_32, 64: _ffi.TILE_ROWS_64}[args.tile_rows]
     timesteps_per_step = int(frames.sum())
 

@@ -55,6 +55,7 @@ extern "C" {
 /* kernel selection, for tests and profiling; default 0 lets the library pick */
 #define TORBI_B200_FORCE_GENERIC (1u << 8)      /* one CTA per sequence, any S                 */
 #define TORBI_B200_FORCE_TILED (1u << 9)        /* batch-tiled max-plus kernel                 */
+#define TORBI_B200_FORCE_WIDE (1u << 11)        /* all SMs per timestep (small batch / long sequence) */
 /* record CUDA events around the forward and backtrace kernels on the caller's
  * stream so torbi_b200_last_timing can report their device time */
 #define TORBI_B200_TIME_KERNELS (1u << 10)

@@ -21,6 +21,7 @@ EPS_FLOOR = 1 << 1
 FORCE_GENERIC = 1 << 8
 FORCE_TILED = 1 << 9
 TIME_KERNELS = 1 << 10
+FORCE_WIDE = 1 << 11
 TILE_ROWS_16 = 1 << 12
 TILE_ROWS_32 = 2 << 12
 TILE_ROWS_64 = 3 << 12

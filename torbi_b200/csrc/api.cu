@@ -198,13 +198,6 @@ int decode_device(const float *observation, const int32_t *batch_frames,
     a.sm_count = info.sm_count;
     a.ws = ws;
     a.frames_ready = frames_ready;
-    {
-        std::vector<int32_t> sorted(B);
-        for (int64_t i = 0; i < B; ++i) sorted[i] = batch_frames[order[i]];
-        a.tile_rows = tiled_choose_rows(sorted.data(), B, S, info.sm_count);
-        if (flags & TORBI_B200_TILE_ROWS_MASK) a.tile_rows = 16 << (((flags & TORBI_B200_TILE_ROWS_MASK) >> 12) - 1);
-    }
-
     const bool timed = flags & TORBI_B200_TIME_KERNELS;
     g_timing.valid = false;
     if (timed) {
@@ -213,13 +206,36 @@ int decode_device(const float *observation, const int32_t *batch_frames,
         if (e != cudaSuccess) return fail_cuda(e, "timing events");
     }
 
-    bool tiled = forward_tiled_supported(a) && !(flags & TORBI_B200_FORCE_GENERIC);
-    if ((flags & TORBI_B200_FORCE_TILED) && !tiled)
-        return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "tiled kernel does not support this shape");
+    // kernel selection: estimated time of the batch-tiled and the wide
+    // decomposition for this length profile, unless a flag forces one
+    std::vector<int32_t> sorted(B);
+    for (int64_t i = 0; i < B; ++i) sorted[i] = batch_frames[order[i]];
+    double tiled_seconds = 0.0;
+    a.tile_rows = tiled_choose_rows(sorted.data(), B, S, info.sm_count, &tiled_seconds);
+    if (flags & TORBI_B200_TILE_ROWS_MASK)
+        a.tile_rows = 16 << (((flags & TORBI_B200_TILE_ROWS_MASK) >> 12) - 1);
+    const bool can_tile = forward_tiled_supported(a), can_wide = forward_wide_supported(a);
+    enum { kGeneric, kTiled, kWide } choice = kGeneric;
+    if (can_tile) choice = kTiled;
+    if (can_wide && (!can_tile || wide_estimate_seconds(sorted.data(), B, S, info.sm_count) < tiled_seconds))
+        choice = kWide;
+    if (flags & (TORBI_B200_FORCE_TILED | TORBI_B200_TILE_ROWS_MASK)) {
+        if (!can_tile) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "tiled kernel does not support this shape");
+        choice = kTiled;
+    }
+    if (flags & TORBI_B200_FORCE_WIDE) {
+        if (!can_wide) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "wide kernel does not support this shape");
+        choice = kWide;
+    }
+    if (flags & TORBI_B200_FORCE_GENERIC) choice = kGeneric;
+    const bool tiled = choice != kGeneric;               // kernels that honour frames_ready
     if (streamed) *streamed = tiled;
-    if (tiled) {
+    if (choice == kTiled) {
         e = launch_forward_tiled(a, stream);
-        g_last_kernel = "forward_tiled";
+        g_last_kernel = a.tile_rows == 64 ? "forward_tiled" : a.tile_rows == 32 ? "forward_tiled_32" : "forward_tiled_16";
+    } else if (choice == kWide) {
+        e = launch_forward_wide(a, stream);
+        g_last_kernel = "forward_wide";
     } else {
         if (frames_ready)
             return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "internal: generic kernel cannot stream");

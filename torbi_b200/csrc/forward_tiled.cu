@@ -496,6 +496,12 @@ __global__ void pad_transition_kernel(const float *__restrict__ src, float *__re
 
 }  // namespace
 
+cudaError_t launch_pad_transition(const ForwardArgs &a, cudaStream_t stream) {
+    pad_transition_kernel<<<a.sm_count * 4, 256, 0, stream>>>(
+        a.transition, a.ws.transition_pad, (int)a.S, (int)padded_dests(a.S), (int)padded_sources(a.S));
+    return cudaGetLastError();
+}
+
 static int64_t tiled_ldp(int64_t S) { return padded_sources(S); }
 static int64_t tiled_sj(int64_t S) { return padded_dests(S); }
 
@@ -529,9 +535,7 @@ static cudaError_t launch_tiled_t(const ForwardArgs &a, cudaStream_t stream) {
     p.NG = std::min(a.sm_count / p.NJT, p.num_batches);
     if ((p.NG + 1) * 32 > (int)kSyncWords) return cudaErrorInvalidValue;
 
-    pad_transition_kernel<<<a.sm_count * 4, 256, 0, stream>>>(a.transition, a.ws.transition_pad,
-                                                              p.S, SJ, p.LDP);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pad_transition(a, stream);
     if (e != cudaSuccess) return e;
 
     auto kernel = forward_tiled_kernel<M, kFlags>;
@@ -560,7 +564,8 @@ static double step_cost(int tm) { return tm == 64 ? 1.0 : tm == 32 ? 0.60 : 0.51
 // Batch height for this call: simulate longest-first list scheduling of the
 // length-sorted batches over the CTA groups for TM = 64 / 32 / 16 and take the
 // smallest makespan.  `frames_sorted` is descending.
-int tiled_choose_rows(const int32_t *frames_sorted, int64_t B, int64_t S, int sm_count) {
+int tiled_choose_rows(const int32_t *frames_sorted, int64_t B, int64_t S, int sm_count,
+                      double *seconds) {
     const int njt = (int)(tiled_sj(S) / TN);
     const int groups_max = std::max(1, sm_count / njt);
     int best_tm = 64;
@@ -576,6 +581,8 @@ int tiled_choose_rows(const int32_t *frames_sorted, int64_t B, int64_t S, int sm
         const double makespan = *std::max_element(load.begin(), load.end());
         if (makespan < best * 0.97) { best = makespan; best_tm = tm; }   // prefer the taller tile on near-ties
     }
+    // one step of a 64-row batch takes 87.5 us at S = 1440 and scales with the K loop
+    if (seconds) *seconds = best * 87.5e-6 * (double)tiled_ldp(S) / 1440.0;
     return best_tm;
 }
 

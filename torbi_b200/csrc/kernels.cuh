@@ -27,7 +27,14 @@ cudaError_t launch_forward_generic(const ForwardArgs &a, cudaStream_t stream);
 // forward_tiled.cu -- batch-tiled max-plus "GEMM" per timestep, persistent grid
 bool forward_tiled_supported(const ForwardArgs &a);
 cudaError_t launch_forward_tiled(const ForwardArgs &a, cudaStream_t stream);
-int tiled_choose_rows(const int32_t *frames_sorted, int64_t B, int64_t S, int sm_count);
+int tiled_choose_rows(const int32_t *frames_sorted, int64_t B, int64_t S, int sm_count,
+                      double *seconds);
+cudaError_t launch_pad_transition(const ForwardArgs &a, cudaStream_t stream);
+
+// forward_wide.cu -- all SMs on every timestep of a few sequences (small batches, long sequences)
+bool forward_wide_supported(const ForwardArgs &a);
+double wide_estimate_seconds(const int32_t *frames_sorted, int64_t B, int64_t S, int sm_count);
+cudaError_t launch_forward_wide(const ForwardArgs &a, cudaStream_t stream);
 
 // backtrace.cu -- ragged backtrace + tail fill (viterbi.cpp:140-160, :219-221)
 cudaError_t launch_backtrace(const Workspace &ws, int32_t *indices, int64_t B, int64_t T,
