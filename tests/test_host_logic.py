@@ -85,6 +85,17 @@ def test_lpt_shards():
     assert torbi_b200.lpt_shards([3, 1], 8) == [[0], [1]]
 
 
+def test_size_bucketed_batches():
+    sizes = [10, 500, 20, 400, 30, 30, 5, 300]
+    batches = torbi_b200.size_bucketed_batches(sizes, batch_size=3, max_padded_bytes=1000)
+    assert sorted(sum(batches, [])) == list(range(len(sizes)))
+    assert all(len(b) <= 3 for b in batches)
+    assert all(len(b) * sizes[b[0]] <= 1000 or len(b) == 1 for b in batches)
+    assert batches[0] == [1, 3]                      # 3 x 500 would exceed the padded budget
+    flat = sum(batches, [])
+    assert [sizes[i] for i in flat] == sorted(sizes, reverse=True)
+
+
 def test_collate_and_separate():
     a = torch.arange(12, dtype=torch.float32).reshape(4, 3)
     b = torch.arange(6, dtype=torch.float32).reshape(2, 3) + 100

@@ -11,8 +11,10 @@ Differences from the reference, all on purpose:
     tensor is never mutated (the reference mutates it in place, core.py:195-197);
     `conversion='host'` reproduces the reference's CPU torch ops exactly instead.
 """
+import concurrent.futures
 import math
 import os
+import queue
 import threading
 from typing import Dict, List, Optional, Sequence, Union
 
@@ -70,6 +72,22 @@ def lpt_shards(costs: Sequence[int], shards: int) -> List[List[int]]:
         bins[k].append(item)
         load[k] += int(costs[item])
     return [sorted(b) for b in bins]
+
+
+def size_bucketed_batches(sizes: Sequence[int], batch_size: int,
+                          max_padded_bytes: int = 2 << 30) -> List[List[int]]:
+    """Batches of file indices, largest files first, at most `batch_size` files and
+    at most `max_padded_bytes` once zero-padded to the largest member (the first of
+    each batch).  Keeps the padded batch of collate() small for long files."""
+    order = sorted(range(len(sizes)), key=lambda i: -int(sizes[i]))
+    batches: List[List[int]] = []
+    for i in order:
+        if batches and len(batches[-1]) < batch_size and \
+                (len(batches[-1]) + 1) * int(sizes[batches[-1][0]]) <= max_padded_bytes:
+            batches[-1].append(i)
+        else:
+            batches.append([i])
+    return batches
 
 
 ###############################################################################
@@ -332,32 +350,46 @@ def from_files_to_files(
         for input_file, output_file in zip(input_files, output_files)}
 
     devices = _resolve_devices(gpu)
+
+    # Results do not depend on batch composition (every item decodes as if alone),
+    # so files are batched by size -- a proxy for frame count -- which keeps the
+    # zero padding of collate() (collate.py:26-31) and the spread of lengths inside a
+    # batch small.  The reference batches in the given order (loader.py:19-25).
+    sizes = [os.path.getsize(file) for file in input_files]
+
     if len(devices) == 1:
         from_dataloader(
-            dataloader=torbi_b200.data.loader(input_files),
+            dataloader=torbi_b200.data.loader(
+                input_files, batch_sampler=size_bucketed_batches(sizes, torbi_b200.BATCH_SIZE)),
             output_files=mapping,
             transition=transition,
             initial=initial,
             log_probs=log_probs,
             gpu=devices[0],
-            num_threads=num_threads)
+            num_threads=num_threads,
+            prefetch=2,
+            save_workers=4)
         return
 
-    sizes = [os.path.getsize(file) for file in input_files]
     shards = lpt_shards(sizes, len(devices))
     errors: List[BaseException] = []
 
     def work(k, items):
         try:
+            shard_files = [input_files[i] for i in items]
             from_dataloader(
-                dataloader=torbi_b200.data.loader([input_files[i] for i in items]),
+                dataloader=torbi_b200.data.loader(
+                    shard_files, batch_sampler=size_bucketed_batches(
+                        [sizes[i] for i in items], torbi_b200.BATCH_SIZE)),
                 output_files=mapping,
                 transition=transition,
                 initial=initial,
                 log_probs=log_probs,
                 gpu=devices[k],
                 num_threads=num_threads,
-                progress=(k == 0))
+                progress=(k == 0),
+                prefetch=2,
+                save_workers=4)
         except BaseException as error:  # noqa: BLE001
             errors.append(error)
 
@@ -375,6 +407,35 @@ def from_files_to_files(
 ###############################################################################
 
 
+def _prefetched(dataloader, depth):
+    """Iterate `dataloader` on a background thread, `depth` batches ahead, with the
+    padded observation pinned so its host->device copy runs at full PCIe rate."""
+    if depth <= 0:
+        yield from dataloader
+        return
+    batches: queue.Queue = queue.Queue(maxsize=depth)
+    done = object()
+
+    def produce():
+        try:
+            for observation, batch_frames, batch_chunks, files in dataloader:
+                if torch.cuda.is_available():
+                    observation = observation.pin_memory()
+                batches.put((observation, batch_frames, batch_chunks, files))
+            batches.put(done)
+        except BaseException as error:  # noqa: BLE001 - re-raised by the consumer
+            batches.put(error)
+
+    threading.Thread(target=produce, daemon=True).start()
+    while True:
+        item = batches.get()
+        if item is done:
+            return
+        if isinstance(item, BaseException):
+            raise item
+        yield item
+
+
 def from_dataloader(
     dataloader: torch.utils.data.DataLoader,
     output_files: Dict[
@@ -385,42 +446,62 @@ def from_dataloader(
     log_probs: bool = False,
     gpu: Gpu = None,
     num_threads: Optional[int] = 1,
-    progress: bool = True
+    progress: bool = True,
+    prefetch: int = 0,
+    save_workers: int = 0
 ) -> None:
     """Decode time-varying categorical distributions from dataloader
     (core.py:376-463): decode each collated batch, then save one int32
-    `(frames,)` tensor per input file."""
+    `(frames,)` tensor per input file.
+
+    `prefetch` > 0 loads / collates / pins that many batches ahead on a background
+    thread while the GPU decodes; `save_workers` > 0 writes the outputs from a
+    thread pool.  Both default to the reference's serial behaviour."""
     bar = _progress(len(dataloader.dataset)) if progress else None
+    savers = concurrent.futures.ThreadPoolExecutor(save_workers) if save_workers > 0 else None
+    pending = []
 
-    for observation, batch_frames, batch_chunks, input_filenames in dataloader:
-
-        indices = from_probabilities(
-            observation=observation,
-            batch_frames=batch_frames,
-            transition=transition,
-            initial=initial,
-            log_probs=log_probs,
-            gpu=gpu,
-            num_threads=num_threads)
-
-        filenames = [output_files[file] for file in input_filenames]
-
-        if torbi_b200.MIN_CHUNK_SIZE is not None:
-            # Combine chunks (core.py:438-448)
-            separated = torbi_b200.data.separate(
-                indices=indices.cpu(), batch_chunks=batch_chunks, batch_frames=batch_frames)
-            for item, filename in zip(separated, filenames):
-                save(item.detach(), filename)
+    def submit(function, *args):
+        if savers is None:
+            function(*args)
         else:
-            # core.py:452-457
-            for item, filename, frames in zip(indices.cpu().detach(), filenames, batch_frames.cpu()):
-                save_masked(item, filename, frames)
+            pending.append(savers.submit(function, *args))
 
+    try:
+        for observation, batch_frames, batch_chunks, input_filenames in _prefetched(dataloader, prefetch):
+
+            indices = from_probabilities(
+                observation=observation,
+                batch_frames=batch_frames,
+                transition=transition,
+                initial=initial,
+                log_probs=log_probs,
+                gpu=gpu,
+                num_threads=num_threads)
+
+            filenames = [output_files[file] for file in input_filenames]
+            indices = indices.cpu().detach()
+
+            if torbi_b200.MIN_CHUNK_SIZE is not None:
+                # Combine chunks (core.py:438-448)
+                separated = torbi_b200.data.separate(
+                    indices=indices, batch_chunks=batch_chunks, batch_frames=batch_frames)
+                for item, filename in zip(separated, filenames):
+                    submit(save, item, filename)
+            else:
+                # core.py:452-457
+                for item, filename, frames in zip(indices, filenames, batch_frames.cpu()):
+                    submit(save_masked, item, filename, frames)
+
+            if bar is not None:
+                bar.update(len(input_filenames))
+        for future in pending:
+            future.result()
+    finally:
+        if savers is not None:
+            savers.shutdown(wait=True)
         if bar is not None:
-            bar.update(len(input_filenames))
-
-    if bar is not None:
-        bar.close()
+            bar.close()
 
 
 def _progress(total):

@@ -17,5 +17,17 @@ class Dataset(torch.utils.data.Dataset):
             observation = torbi_b200.chunk(observation)
         return observation, input_file
 
+    def __getitems__(self, indices):
+        """Batched fetch used by the DataLoader: the files of one batch are read
+        by a small thread pool (torch.load spends its time in file reads and
+        copies that release the GIL), results in the given order."""
+        if len(indices) < 4:
+            return [self[i] for i in indices]
+        import concurrent.futures
+        import os
+        workers = min(16, len(indices), os.cpu_count() or 1)
+        with concurrent.futures.ThreadPoolExecutor(workers) as pool:
+            return list(pool.map(self.__getitem__, indices))
+
     def __len__(self):
         return len(self.input_files)
