@@ -1,0 +1,31 @@
+"""Small decodes through every kernel for compute-sanitizer (memcheck / racecheck /
+initcheck / synccheck):  compute-sanitizer --tool memcheck python tools/sanitize.py"""
+import pathlib
+import sys
+
+import numpy as np
+import torch
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / 'tests' / 'golden'))
+import cases  # noqa: E402
+import torbi_b200  # noqa: E402
+from torbi_b200 import _ffi  # noqa: E402
+from oracle import oracle  # noqa: E402
+
+rng = np.random.default_rng(0)
+for (B, T, S) in [(5, 6, 200), (70, 4, 96), (3, 5, 333)]:
+    obs = cases.log_softmax(rng.standard_normal((B, T, S)))
+    A = cases.log_softmax(rng.standard_normal((S, S)))
+    init = cases.log_softmax(rng.standard_normal((S,)))
+    frames = rng.integers(1, T + 1, size=B).astype(np.int32)
+    frames[0] = T
+    want = oracle.c_decode(obs, frames, A, init)
+    for name, flag in [('generic', _ffi.FORCE_GENERIC), ('tiled64', _ffi.TILE_ROWS_64), ('tiled32', _ffi.TILE_ROWS_32),
+                       ('tiled16', _ffi.TILE_ROWS_16), ('wide', _ffi.FORCE_WIDE)]:
+        got = torbi_b200.decode(torch.from_numpy(obs).cuda(), torch.from_numpy(frames), torch.from_numpy(A).cuda(),
+                                torch.from_numpy(init).cuda(), flags=flag | _ffi.EPS_FLOOR)
+        torch.cuda.synchronize()
+        assert np.array_equal(got.cpu().numpy(), want), (name, B, T, S)
+        print('ok', name, (B, T, S), flush=True)

@@ -156,7 +156,7 @@ template <int TM, bool kFullTile>
 __device__ __forceinline__ void rescan_tile(const float *best_tile, uint16_t *bp_tile,
                                             const int *slot_frames, const float *P_rows,
                                             const float *A_rows, int LDP, int cols_valid, int S, int t) {
-    constexpr int kBatch = 10;
+    constexpr int kBatch = 20;
     constexpr int kRowsPerWarp = TM / (kThreads / kWarp);
     const int lane = threadIdx.x % kWarp, warp = threadIdx.x / kWarp;
     const int sub = lane >> 3, q4 = (lane & 7) * 4;
@@ -197,9 +197,14 @@ __device__ __forceinline__ void rescan_tile(const float *best_tile, uint16_t *bp
                 key = min(key, __shfl_xor_sync(kFullMask, key, 2));
                 key = min(key, __shfl_xor_sync(kFullMask, key, 4));
                 // (key == 64 only for NaN input, outside the parity contract)
-                if ((lane & 7) == 0 && (kFullTile || (cb + u) * 4 + sub < cols_valid))
-                    bp_row[(cb + u) * 4] = (uint16_t)min(k0[u] + (int)key, S - 1);
+                k0[u] = min(k0[u] + (int)key, S - 1);
             }
+            __syncwarp();       // every lane has read its chunk ids before they are overwritten
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u)
+                if ((lane & 7) == 0 && (kFullTile || (cb + u) * 4 + sub < cols_valid))
+                    bp_row[(cb + u) * 4] = (uint16_t)k0[u];
+            __syncwarp();
         }
     }
 }
@@ -431,12 +436,14 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             // ---- exact argmax while the rest of the group catches up: lowest s in the
             //      winning chunk with P[s] + A[j][s] == max.  8 lanes share one output
             //      (a float4 of the chunk each), so every load is a coalesced 128-byte row.
+#ifndef TORBI_EXPERIMENT_SKIP_RESCAN      // timing experiments only: results are wrong without it
             if (j0 + TN <= S)
                 rescan_tile<TM, true>(best_tile, bp_tile, slot_frames, P_cur + row0 * LDP, p.transition + (int64_t)j0 * LDP,
                                   LDP, S - j0, S, t);
             else
                 rescan_tile<TM, false>(best_tile, bp_tile, slot_frames, P_cur + row0 * LDP, p.transition + (int64_t)j0 * LDP,
                                    LDP, S - j0, S, t);
+#endif
             __syncthreads();
 
             // ---- backpointers: coalesced, vectorised uint16 stores ----
