@@ -53,6 +53,7 @@ def parse_args():
     parser.add_argument('--no-cpu-baseline', action='store_true')
     parser.add_argument('--kernel', default='auto', choices=['auto', 'generic', 'tiled', 'wide'])
     parser.add_argument('--tile-rows', type=int, default=0, choices=[0, 16, 32, 64])
+    parser.add_argument('--ws', action='store_true', help='warp-specialised tiled kernel')
     return parser.parse_args()
 
 
@@ -264,6 +265,8 @@ def bench_graft(args):
     flags = _ffi.EPS_FLOOR | _ffi.TIME_KERNELS
     flags |= {'auto': 0, 'generic': _ffi.FORCE_GENERIC, 'tiled': _ffi.FORCE_TILED, 'wide': _ffi.FORCE_WIDE}[args.kernel]
     flags |= {0: 0, 16: _ffi.TILE_ROWS_16, 32: _ffi.TILE_ROWS_32, 64: _ffi.TILE_ROWS_64}[args.tile_rows]
+    if args.ws:
+        flags |= _ffi.TILED_WS
     timesteps_per_step = int(frames.sum())
 
     fwd_ms, back_ms = [], []

@@ -64,6 +64,8 @@ extern "C" {
 #define TORBI_B200_TILE_ROWS_16 (1u << 12)
 #define TORBI_B200_TILE_ROWS_32 (2u << 12)
 #define TORBI_B200_TILE_ROWS_64 (3u << 12)
+/* use the warp-specialised variant of the tiled kernel (64-row batches, S % 8 == 0) */
+#define TORBI_B200_TILED_WS (1u << 14)
 
 TORBI_B200_API int torbi_b200_abi_version(void);
 

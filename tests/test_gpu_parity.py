@@ -12,7 +12,8 @@ from torbi_b200 import _ffi
 pytestmark = pytest.mark.gpu
 
 KERNELS = {'auto': 0, 'generic': _ffi.FORCE_GENERIC, 'tiled16': _ffi.TILE_ROWS_16,
-           'tiled32': _ffi.TILE_ROWS_32, 'tiled64': _ffi.TILE_ROWS_64, 'wide': _ffi.FORCE_WIDE}
+           'tiled32': _ffi.TILE_ROWS_32, 'tiled64': _ffi.TILE_ROWS_64, 'wide': _ffi.FORCE_WIDE,
+           'tiled64ws': _ffi.TILE_ROWS_64 | _ffi.TILED_WS}
 
 
 def bits(a):

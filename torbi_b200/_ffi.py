@@ -25,6 +25,7 @@ FORCE_WIDE = 1 << 11
 TILE_ROWS_16 = 1 << 12
 TILE_ROWS_32 = 2 << 12
 TILE_ROWS_64 = 3 << 12
+TILED_WS = 1 << 14
 
 ABI_VERSION = 1
 

@@ -230,7 +230,10 @@ int decode_device(const float *observation, const int32_t *batch_frames,
     if (flags & TORBI_B200_FORCE_GENERIC) choice = kGeneric;
     const bool tiled = choice != kGeneric;               // kernels that honour frames_ready
     if (streamed) *streamed = tiled;
-    if (choice == kTiled) {
+    if (choice == kTiled && (flags & TORBI_B200_TILED_WS) && forward_tiled_ws_supported(a)) {
+        e = launch_forward_tiled_ws(a, stream);
+        g_last_kernel = "forward_tiled_ws";
+    } else if (choice == kTiled) {
         e = launch_forward_tiled(a, stream);
         g_last_kernel = a.tile_rows == 64 ? "forward_tiled" : a.tile_rows == 32 ? "forward_tiled_32" : "forward_tiled_16";
     } else if (choice == kWide) {

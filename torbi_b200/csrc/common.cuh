@@ -47,7 +47,7 @@ struct Workspace {
     int32_t *order;         // (B,)  items sorted by length, longest first
     int32_t *final_state;   // (B,)  argmax of the final forward scores
     uint32_t *sync;         // scheduling / barrier words (zeroed per call)
-    float *score[3];        // rotating forward-score buffers, (pad_batch, padded_sources) each
+    float *score[4];        // rotating forward-score buffers, (pad_batch, padded_sources) each
     float *transition_pad;  // (padded_dests, padded_sources) copy, -inf outside (S,S)
     uint16_t *backptr;      // (B, T, S) uint16 backpointers; row 0 unused
     size_t bytes;
@@ -83,6 +83,7 @@ inline Workspace carve_workspace(void *base, int64_t B, int64_t T, int64_t S) {
     w.score[0] = static_cast<float *>(take(sizeof(float) * Bp * Sp));
     w.score[1] = static_cast<float *>(take(sizeof(float) * Bp * Sp));
     w.score[2] = static_cast<float *>(take(sizeof(float) * Bp * Sp));
+    w.score[3] = static_cast<float *>(take(sizeof(float) * Bp * Sp));
     w.transition_pad = static_cast<float *>(take(sizeof(float) * padded_dests(S) * Sp));
     w.backptr = static_cast<uint16_t *>(take(sizeof(uint16_t) * B * T * S));
     w.bytes = off;

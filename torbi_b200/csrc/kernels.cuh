@@ -31,6 +31,10 @@ int tiled_choose_rows(const int32_t *frames_sorted, int64_t B, int64_t S, int sm
                       double *seconds);
 cudaError_t launch_pad_transition(const ForwardArgs &a, cudaStream_t stream);
 
+// forward_tiled_ws.cu -- warp-specialised variant of the tiled kernel for 64-row batches
+bool forward_tiled_ws_supported(const ForwardArgs &a);
+cudaError_t launch_forward_tiled_ws(const ForwardArgs &a, cudaStream_t stream);
+
 // forward_wide.cu -- all SMs on every timestep of a few sequences (small batches, long sequences)
 bool forward_wide_supported(const ForwardArgs &a);
 double wide_estimate_seconds(const int32_t *frames_sorted, int64_t B, int64_t S, int sm_count);
