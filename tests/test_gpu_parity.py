@@ -227,6 +227,12 @@ def test_multi_gpu_list_api(oracle):
     assert np.array_equal(got.cpu().numpy(), want)
 
 
+def test_dispatcher_op_on_gpu(oracle):
+    obs, frames, A, init = random_problem(41, 5, 12, 160)
+    got = torch.ops.torbi_b200.viterbi_decode(cuda(obs), torch.from_numpy(frames), cuda(A), cuda(init))
+    assert np.array_equal(got.cpu().numpy(), oracle.c_decode(obs, frames, A, init))
+
+
 def test_errors_on_gpu():
     obs = torch.rand(2, 4, 5, device='cuda:0')
     A, init = torch.rand(5, 5, device='cuda:0'), torch.rand(5, device='cuda:0')

@@ -168,6 +168,32 @@ def test_cli_and_configure(tmp_path):
         torbi_b200.BATCH_SIZE, torbi_b200.MIN_CHUNK_SIZE = 512, None
 
 
+def test_dispatcher_op_schema_and_meta_kernel():
+    # same schema as the reference operator (ops.cpp:16-18), traceable through the meta kernel
+    op = torch.ops.torbi_b200.viterbi_decode
+    schema = str(op.default._schema)
+    assert 'Tensor observation, Tensor batch_frames, Tensor transition, Tensor initial' in schema
+    out = op(torch.empty(3, 7, 5, device='meta'), torch.empty(3, device='meta', dtype=torch.int32),
+             torch.empty(5, 5, device='meta'), torch.empty(5, device='meta'))
+    assert out.shape == (3, 7) and out.dtype == torch.int32
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        op(torch.rand(1, 3, 3), torch.tensor([3], dtype=torch.int32), torch.rand(3, 3), torch.rand(3))
+
+
+def test_evaluate_transition_and_rpa():
+    import cases
+    A = torbi_b200.evaluate.pitch_transition(96)
+    assert torch.allclose(A.sum(dim=1), torch.ones(96))
+    assert (A[0, 90:] == 0).all() and A[40, 40] == A[40].max()
+    # same recipe as the fixture generator used for the golden vectors
+    width = torbi_b200.evaluate.MAX_OCTAVES_PER_SECOND * torbi_b200.evaluate.HOPSIZE / \
+        torbi_b200.evaluate.SAMPLE_RATE * (torbi_b200.evaluate.OCTAVE / torbi_b200.evaluate.CENTS_PER_BIN) + 1
+    assert np.allclose(A.numpy(), cases.triangular_transition(96, width), atol=1e-7)
+    result = torbi_b200.evaluate.agreement(
+        [torch.tensor([1, 2, 3, 10])], [torch.tensor([1, 3, 5, 10])])
+    assert result == {'rpa': {'0': 0.5, '1': 0.75, '2': 1.0}}
+
+
 def test_product_never_imports_the_oracle():
     # the oracle is test infrastructure: nothing under torbi_b200/ may reference it
     for path in (ROOT / 'torbi_b200').rglob('*'):

@@ -42,5 +42,7 @@ from .core import *                                  # noqa: E402,F401,F403
 from .core import lpt_shards, size_bucketed_batches  # noqa: E402,F401
 from .chunk import chunk                             # noqa: E402
 from . import data                                   # noqa: E402
+from . import evaluate                               # noqa: E402
+from . import ops                                    # noqa: E402,F401  (registers torch.ops.torbi_b200)
 
 LIBRARY = pathlib.Path(_ffi.LIBRARY)
