@@ -138,6 +138,24 @@ __device__ __forceinline__ void load_stage_part(float *stage, const float *gA, c
                 cp_async16(sP + q * 10 * LDS_, gP + q * row_stride10);
     }
 }
+// whole-stage halves used at the step boundary: the transition rows do not depend on
+// the group's score exchange and are issued before the barrier wait, the score rows after
+template <int TM>
+__device__ __forceinline__ void load_stage_A(float *stage, const float *gA, int64_t row_stride10) {
+    if (threadIdx.x < kLoaders) {
+        float *sA = stage + TM * LDS_;
+#pragma unroll
+        for (int q = 0; q < TN / 10; ++q) cp_async16(sA + q * 10 * LDS_, gA + q * row_stride10);
+    }
+}
+template <int TM>
+__device__ __forceinline__ void load_stage_P(float *stage, const float *gP, int64_t row_stride10, int r0) {
+    if (threadIdx.x < kLoaders) {
+#pragma unroll
+        for (int q = 0; q < (TM + 9) / 10; ++q)
+            if (q * 10 + 9 < TM || r0 + q * 10 < TM) cp_async16(stage + q * 10 * LDS_, gP + q * row_stride10);
+    }
+}
 template <int TM>
 __device__ __forceinline__ void load_stage(float *stage, const float *gA, const float *gP,
                                            int64_t row_stride10, int r0) {
@@ -303,17 +321,10 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
         group_arrive(counter);
         group_wait(counter, barriers);
 
-        int buf = 0;                                    // buffer holding P_{t-1}
-        for (int t = 1; t < batch_frames; ++t) {
-            // three rotating buffers: a CTA that is already publishing step t+1 never
-            // writes the buffer a slower CTA of the group still re-scans for step t
-            const int buf_new = buf == 2 ? 0 : buf + 1;
-            const float *P_cur = p.score0 + buf * p.score_stride;
-            float *P_new = p.score0 + buf_new * p.score_stride;
-            buf = buf_new;
-            const float *ld_P = P_cur + (row0 + ld_r0) * LDP + ld_c4 * 4;
-
-            // emission tile for this step (raw; converted when consumed)
+        // Everything step `t` needs that does not depend on the other CTAs: its emission tile
+        // (raw; converted when consumed) and the transition rows of pipeline stages 0 and 1.
+        // Issued without a commit: they join the step's first cp.async group.
+        auto prefetch_step = [&](int t) {
             wait_for_frame(t);
             if (obs_vec) {
                 for (int idx = tid; idx < TM * (TN / 4); idx += kThreads) {
@@ -331,11 +342,26 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                         tile[idx] = __ldg(p.observation + ((int64_t)item * p.T + t) * S + j0 + c);
                 }
             }
-            // prologue: stages 0 and 1
-            load_stage<TM>(ring + ld_smem, ld_A, ld_P, ld_stride10, ld_r0);
+            load_stage_A<TM>(ring + ld_smem, ld_A, ld_stride10);
+            if (nstages > 1) load_stage_A<TM>(ring + kStageFloats + ld_smem, ld_A + KS, ld_stride10);
+        };
+        if (batch_frames > 1) prefetch_step(1);
+
+        int buf = 0;                                    // buffer holding P_{t-1}
+        for (int t = 1; t < batch_frames; ++t) {
+            // three rotating buffers: a CTA that is already publishing step t+1 never
+            // writes the buffer a slower CTA of the group still re-scans for step t
+            const int buf_new = buf == 2 ? 0 : buf + 1;
+            const float *P_cur = p.score0 + buf * p.score_stride;
+            float *P_new = p.score0 + buf_new * p.score_stride;
+            buf = buf_new;
+            const float *ld_P = P_cur + (row0 + ld_r0) * LDP + ld_c4 * 4;
+
+            // the emission tile and the transition rows of stages 0 / 1 were prefetched before
+            // the exchange wait (prefetch_step); only the score rows are left
+            load_stage_P<TM>(ring + ld_smem, ld_P, ld_stride10, ld_r0);
             cp_async_commit();
-            if (nstages > 1)
-                load_stage<TM>(ring + kStageFloats + ld_smem, ld_A + KS, ld_P + KS, ld_stride10, ld_r0);
+            if (nstages > 1) load_stage_P<TM>(ring + kStageFloats + ld_smem, ld_P + KS, ld_stride10, ld_r0);
             cp_async_commit();
 
             float cur[M][N];
@@ -432,6 +458,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             }
             barriers += p.NJT;
             group_arrive(counter);
+            if (t + 1 < batch_frames) prefetch_step(t + 1);   // `tile` is free: the publish above was its last reader
 
             // ---- exact argmax while the rest of the group catches up: lowest s in the
             //      winning chunk with P[s] + A[j][s] == max.  8 lanes share one output
