@@ -3,9 +3,9 @@
 // every timestep of a few sequences.
 //
 //   * persistent cooperative grid of NC <= #SM CTAs; CTA c owns the destination
-//     states [c*R, c*R+R) and keeps its slice of the transition matrix RESIDENT in
-//     shared memory for the whole call when it fits (S = 1440: 10 rows, 58 KB);
-//     otherwise the slice is streamed from L2 every step (S = 4096);
+//     states [c*R, c*R+R) and keeps as many rows of its transition slice as fit
+//     RESIDENT in shared memory for the whole call (S = 1440: all 10 rows, 58 KB;
+//     S = 4096: 11 of 28 rows), streaming the rest from L2 every step;
 //   * up to BC <= 16 sequences advance in lockstep; each step every CTA pulls their
 //     previous scores (BC x S floats) from L2 into shared memory, one warp computes
 //     a destination row for all BC sequences, and the grid meets at a counter
@@ -44,6 +44,7 @@ struct WideParams {
     const int32_t *frames_ready;
     int64_t T;
     int B, S, LDP, NC, R;
+    int resident_rows;          // leading rows of each CTA's transition slice kept in shared memory
 };
 
 __device__ __forceinline__ unsigned wide_ld_acquire(const unsigned *p) {
@@ -67,12 +68,12 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target)
     __syncthreads();
 }
 
-template <int BC, bool kResident, uint32_t kFlags>
+template <int BC, uint32_t kFlags>
 __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const WideParams p) {
     extern __shared__ __align__(16) float smem[];
     const int S = p.S, LDP = p.LDP, R = p.R;
     float *Ps = smem;                                    // [BC][LDP] previous scores
-    float *As = smem + BC * LDP;                         // [R][LDP] transition slice (if resident)
+    float *As = smem + BC * LDP;                         // [resident_rows][LDP] transition slice
     __shared__ int slot_item[BC], slot_frames[BC];
     __shared__ int ready_shared;
 
@@ -93,8 +94,9 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
         }
     };
 
-    if (kResident) {
-        for (int idx = tid; idx < (j_end - j_begin) * (LDP / 4); idx += kWideThreads) {
+    const int resident_rows = min(p.resident_rows, j_end - j_begin);
+    {
+        for (int idx = tid; idx < resident_rows * (LDP / 4); idx += kWideThreads) {
             const int r = idx / (LDP / 4), q = idx % (LDP / 4);
             reinterpret_cast<float4 *>(As + r * LDP)[q] =
                 __ldg(reinterpret_cast<const float4 *>(p.transition + (int64_t)(j_begin + r) * LDP) + q);
@@ -139,14 +141,12 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
             wait_for_frame(t);
 
             // previous scores of the group -> shared memory (L2 only: rewritten every step)
+#pragma unroll 4
             for (int idx = tid; idx < nb * (LDP / 4); idx += kWideThreads)
                 reinterpret_cast<float4 *>(Ps)[idx] = __ldcg(reinterpret_cast<const float4 *>(P_cur) + idx);
             __syncthreads();
 
             for (int j = j_begin + warp; j < j_end; j += kWideWarps) {
-                const float4 *arow = kResident
-                    ? reinterpret_cast<const float4 *>(As + (j - j_begin) * LDP)
-                    : reinterpret_cast<const float4 *>(p.transition + (int64_t)j * LDP);
                 // emissions (and carried scores of finished sequences) fetched early by lane b
                 float emit = 0.f;
                 if (lane < nb) {
@@ -160,27 +160,45 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
                 const bool has_groups = lane < LDP / 4;          // S <= 96: lanes 24..31 own no source state
 #pragma unroll
                 for (int b = 0; b < BC; ++b) { best[b] = -INFINITY; grp[b] = has_groups ? lane : 0; }
-                for (int q = lane; q < LDP / 4; q += kWarp) {
-                    const float4 a = kResident ? arow[q] : __ldg(arow + q);
+                int arg_b[BC];
+                // the scan, parametrised on where the transition row lives: resident rows are
+                // read with LDS, the rest of the slice streams from L2 through the read-only path
+                auto scan_row = [&](auto load_a) {
+                    for (int q = lane; q < LDP / 4; q += kWarp) {
+                        const float4 a = load_a(q);
 #pragma unroll
-                    for (int b = 0; b < BC; ++b) {
-                        if (b < nb) {
-                            const float4 pv = reinterpret_cast<const float4 *>(Ps + b * LDP)[q];
-                            const float m = fmaxf(fmaxf(pv.x + a.x, pv.y + a.y), fmaxf(pv.z + a.z, pv.w + a.w));
-                            if (m > best[b]) { best[b] = m; grp[b] = q; }     // first group reaching the max
+                        for (int b = 0; b < BC; ++b) {
+                            if (b < nb) {
+                                const float4 pv = reinterpret_cast<const float4 *>(Ps + b * LDP)[q];
+                                const float m = fmaxf(fmaxf(pv.x + a.x, pv.y + a.y), fmaxf(pv.z + a.z, pv.w + a.w));
+                                if (m > best[b]) { best[b] = m; grp[b] = q; }     // first group reaching the max
+                            }
                         }
                     }
+#pragma unroll
+                    for (int b = 0; b < BC; ++b) {
+                        // lowest index inside the lane's winning group
+                        const float4 a = load_a(grp[b]);
+                        const float4 pv = reinterpret_cast<const float4 *>(Ps + (b < nb ? b : 0) * LDP)[grp[b]];
+                        int arg = 4 * grp[b] + 3;
+                        if (pv.z + a.z == best[b]) arg = 4 * grp[b] + 2;
+                        if (pv.y + a.y == best[b]) arg = 4 * grp[b] + 1;
+                        if (pv.x + a.x == best[b]) arg = 4 * grp[b];
+                        arg_b[b] = arg;
+                    }
+                };
+                if (j - j_begin < resident_rows) {
+                    const float4 *arow = reinterpret_cast<const float4 *>(As + (j - j_begin) * LDP);
+                    scan_row([&](int q) { return arow[q]; });
+                } else {
+                    const float4 *arow = reinterpret_cast<const float4 *>(p.transition + (int64_t)j * LDP);
+                    scan_row([&](int q) { return arow[q]; });   // plain LDG: measured 2x faster here than the .nc path
                 }
 #pragma unroll
                 for (int b = 0; b < BC; ++b) {
                     if (b >= nb) continue;
-                    // lowest index inside the lane's winning group, then across lanes
-                    const float4 a = kResident ? arow[grp[b]] : __ldg(arow + grp[b]);
-                    const float4 pv = reinterpret_cast<const float4 *>(Ps + b * LDP)[grp[b]];
-                    int arg = 4 * grp[b] + 3;
-                    if (pv.z + a.z == best[b]) arg = 4 * grp[b] + 2;
-                    if (pv.y + a.y == best[b]) arg = 4 * grp[b] + 1;
-                    if (pv.x + a.x == best[b]) arg = 4 * grp[b];
+                    // ... then across lanes
+                    int arg = arg_b[b];
                     if (!has_groups) arg = 0x7fffffff;            // (-inf, INT_MAX) never wins a tie
                     float v = best[b];
 #pragma unroll
@@ -227,7 +245,8 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
 
 struct WideGeometry {
     int NC, R, BC;
-    bool resident;
+    int resident_rows;     // of the R rows a CTA owns
+    bool resident;         // all of them
     size_t smem;
 };
 
@@ -241,8 +260,10 @@ WideGeometry wide_geometry(int64_t B, int64_t S, int sm_count) {
     g.BC = B > 4 ? 16 : B > 1 ? 4 : 1;
     while (g.BC > 1 && sizeof(float) * g.BC * ldp > budget) g.BC /= 4;
     const size_t scores = sizeof(float) * g.BC * ldp;
-    g.resident = scores + slice <= budget;
-    g.smem = scores + (g.resident ? slice : 0);
+    (void)slice;
+    g.resident_rows = scores < budget ? (int)std::min<size_t>(g.R, (budget - scores) / (sizeof(float) * ldp)) : 0;
+    g.resident = g.resident_rows == g.R;
+    g.smem = scores + sizeof(float) * ldp * g.resident_rows;
     return g;
 }
 
@@ -256,22 +277,24 @@ bool forward_wide_supported(const ForwardArgs &a) {
 // Estimated seconds for the wide kernel: per step a fixed exchange + barrier cost
 // plus the max-plus work of the sequences still running (calibrated on the B200).
 double wide_estimate_seconds(const int32_t *frames_sorted, int64_t B, int64_t S, int sm_count) {
-    // B200 measurements (tools/calibrate_kernels.sh): S = 1440 resident: 3.1 / 6.5 / 19.9 us per
-    // step for 1 / 4 / 16 sequences; S = 4096 streamed: 17.8 / 31.4 us for 1 / 4.
+    // B200 measurements (tools/calibrate_kernels.sh): S = 1440 fully resident: 3.1 / 6.6 / 20.0 us
+    // per step for 1 / 4 / 16 sequences; S = 4096 (11 of 28 rows resident): 8.2 / 30.6 us for 1 / 4.
     const WideGeometry g = wide_geometry(B, S, sm_count);
     const double ldp = (double)padded_sources(S);
     const double rounds = (g.R + kWideWarps - 1) / kWideWarps;             // rows per warp
     const double per_sequence_us = rounds * ldp * 0.00072;
-    const double slice_stream_us = g.resident ? 0.0 : 4.0 * (double)padded_dests(S) * ldp / 5.0e6;  // ~5 TB/s of L2
+    const double streamed = 1.0 - (double)g.resident_rows / g.R;
+    const double slice_stream_us = 4.0 * (double)padded_dests(S) * ldp * streamed / 5.0e6;   // ~5 TB/s of L2
     double total = 0.0;
     for (int64_t first = 0; first < B; first += g.BC) {
         const int nb = (int)std::min<int64_t>(g.BC, B - first);
-        total += frames_sorted[first] * (2.0 + slice_stream_us + per_sequence_us * nb);
+        // streaming the non-resident rows overlaps the per-sequence scans
+        total += frames_sorted[first] * (2.0 + std::max(slice_stream_us, per_sequence_us * nb));
     }
     return total * 1e-6;
 }
 
-template <int BC, bool kResident>
+template <int BC>
 static cudaError_t launch_wide_t(const ForwardArgs &a, const WideParams &p, size_t smem,
                                  cudaStream_t stream) {
     void *args[] = {(void *)&p};
@@ -281,10 +304,10 @@ static cudaError_t launch_wide_t(const ForwardArgs &a, const WideParams &p, size
         return cudaLaunchCooperativeKernel((void *)kernel, dim3(p.NC), dim3(kWideThreads), args, smem, stream);
     };
     switch (a.flags & 3u) {
-        case 0: return launch(forward_wide_kernel<BC, kResident, 0>);
-        case 1: return launch(forward_wide_kernel<BC, kResident, 1>);
-        case 2: return launch(forward_wide_kernel<BC, kResident, 2>);
-        default: return launch(forward_wide_kernel<BC, kResident, 3>);
+        case 0: return launch(forward_wide_kernel<BC, 0>);
+        case 1: return launch(forward_wide_kernel<BC, 1>);
+        case 2: return launch(forward_wide_kernel<BC, 2>);
+        default: return launch(forward_wide_kernel<BC, 3>);
     }
 }
 
@@ -309,16 +332,12 @@ cudaError_t launch_forward_wide(const ForwardArgs &a, cudaStream_t stream) {
     p.LDP = (int)padded_sources(a.S);
     p.NC = g.NC;
     p.R = g.R;
+    p.resident_rows = g.resident_rows;
     cudaError_t e = launch_pad_transition(a, stream);
     if (e != cudaSuccess) return e;
-    if (g.resident) {
-        if (g.BC == 1) return launch_wide_t<1, true>(a, p, g.smem, stream);
-        if (g.BC == 4) return launch_wide_t<4, true>(a, p, g.smem, stream);
-        return launch_wide_t<16, true>(a, p, g.smem, stream);
-    }
-    if (g.BC == 1) return launch_wide_t<1, false>(a, p, g.smem, stream);
-    if (g.BC == 4) return launch_wide_t<4, false>(a, p, g.smem, stream);
-    return launch_wide_t<16, false>(a, p, g.smem, stream);
+    if (g.BC == 1) return launch_wide_t<1>(a, p, g.smem, stream);
+    if (g.BC == 4) return launch_wide_t<4>(a, p, g.smem, stream);
+    return launch_wide_t<16>(a, p, g.smem, stream);
 }
 
 }  // namespace torbi_b200
