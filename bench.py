@@ -54,6 +54,7 @@ def parse_args():
     parser.add_argument('--kernel', default='auto', choices=['auto', 'generic', 'tiled', 'wide'])
     parser.add_argument('--tile-rows', type=int, default=0, choices=[0, 16, 32, 64])
     parser.add_argument('--ws', action='store_true', help='warp-specialised tiled kernel')
+    parser.add_argument('--banded', action='store_true', help='exact banded-transition fast path (not the contract metric)')
     return parser.parse_args()
 
 
@@ -267,6 +268,8 @@ def bench_graft(args):
     flags |= {0: 0, 16: _ffi.TILE_ROWS_16, 32: _ffi.TILE_ROWS_32, 64: _ffi.TILE_ROWS_64}[args.tile_rows]
     if args.ws:
         flags |= _ffi.TILED_WS
+    if args.banded:
+        flags |= _ffi.BANDED
     timesteps_per_step = int(frames.sum())
 
     fwd_ms, back_ms = [], []

@@ -64,6 +64,11 @@ extern "C" {
 #define TORBI_B200_TILE_ROWS_16 (1u << 12)
 #define TORBI_B200_TILE_ROWS_32 (2u << 12)
 #define TORBI_B200_TILE_ROWS_64 (3u << 12)
+/* exact fast path for banded transition matrices (tiled kernel): a device-side pass finds,
+ * per tile of destination states, the source window outside which every entry equals one
+ * constant; the dense loop runs over the window only and the rest is a first-occurrence max
+ * of P[s] + constant.  Bit-identical results for ANY matrix, faster when it is banded. */
+#define TORBI_B200_BANDED (1u << 15)
 /* use the warp-specialised variant of the tiled kernel (64-row batches, S % 8 == 0) */
 #define TORBI_B200_TILED_WS (1u << 14)
 

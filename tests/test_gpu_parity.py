@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 
 KERNELS = {'auto': 0, 'generic': _ffi.FORCE_GENERIC, 'tiled16': _ffi.TILE_ROWS_16,
            'tiled32': _ffi.TILE_ROWS_32, 'tiled64': _ffi.TILE_ROWS_64, 'wide': _ffi.FORCE_WIDE,
-           'tiled64ws': _ffi.TILE_ROWS_64 | _ffi.TILED_WS}
+           'tiled64ws': _ffi.TILE_ROWS_64 | _ffi.TILED_WS, 'banded': _ffi.BANDED,
+           'banded16': _ffi.BANDED | _ffi.TILE_ROWS_16}
 
 
 def bits(a):
@@ -137,6 +138,28 @@ def test_decode_matches_oracle(shape, kernel, oracle):
     indices, posterior = gpu_decode(obs, frames, A, init, flags=KERNELS[kernel])
     assert np.array_equal(indices, want_idx)
     assert np.array_equal(bits(posterior), bits(want_post))
+
+
+@pytest.mark.parametrize('outside', [-87.33655, -np.inf, -3.0])
+@pytest.mark.parametrize('states,width', [(1440, 87.2), (1000, 3.0), (333, 40.5), (2048, 300.0)])
+def test_banded_fast_path_is_exact(states, width, outside, oracle):
+    """Banded matrices with different constants outside the band, quantised so that ties
+    between in-window and out-of-window sources occur; banded == dense == oracle."""
+    rng = np.random.default_rng(states)
+    B, T = 7, 12
+    i = np.arange(states)
+    band = np.abs(i[:, None] - i[None, :]) < width
+    A = np.where(band, np.round(rng.standard_normal((states, states)) * 2) / 2 - 1.0, outside).astype(np.float32)
+    A[5, :] = np.float32(outside)                                  # a row with nothing in its band
+    obs = (np.round(cases.log_softmax(rng.standard_normal((B, T, states))) * 2) / 2).astype(np.float32)
+    init = cases.log_softmax(rng.standard_normal((states,)))
+    frames = rng.integers(1, T + 1, size=B).astype(np.int32)
+    frames[0] = T
+    want_idx, want_post = oracle.c_decode(obs, frames, A, init, exact_scan=False, want_posterior=True)
+    for flags in (_ffi.BANDED, _ffi.BANDED | _ffi.TILE_ROWS_32, 0):
+        indices, posterior = gpu_decode(obs, frames, A, init, flags=flags)
+        assert np.array_equal(indices, want_idx)
+        assert np.array_equal(bits(posterior), bits(want_post))
 
 
 def test_padding_is_never_read(oracle):

@@ -29,7 +29,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_flag_values_match_header():
     header = (ROOT / 'include' / 'torbi_b200.h').read_text()
-    for name in ('OBS_IS_PROBABILITY', 'EPS_FLOOR', 'FORCE_GENERIC', 'FORCE_TILED', 'FORCE_WIDE', 'TIME_KERNELS'):
+    for name in ('OBS_IS_PROBABILITY', 'EPS_FLOOR', 'FORCE_GENERIC', 'FORCE_TILED', 'FORCE_WIDE', 'TIME_KERNELS',
+                 'TILED_WS', 'BANDED'):
         shift = int(re.search(rf'#define TORBI_B200_{name} \(1u << (\d+)\)', header).group(1))
         assert getattr(_ffi, name) == 1 << shift
     for name, value in (('TILE_ROWS_16', 1), ('TILE_ROWS_32', 2), ('TILE_ROWS_64', 3)):

@@ -26,6 +26,7 @@ TILE_ROWS_16 = 1 << 12
 TILE_ROWS_32 = 2 << 12
 TILE_ROWS_64 = 3 << 12
 TILED_WS = 1 << 14
+BANDED = 1 << 15
 
 ABI_VERSION = 1
 

@@ -219,7 +219,7 @@ int decode_device(const float *observation, const int32_t *batch_frames,
     if (can_tile) choice = kTiled;
     if (can_wide && (!can_tile || wide_estimate_seconds(sorted.data(), B, S, info.sm_count) < tiled_seconds))
         choice = kWide;
-    if (flags & (TORBI_B200_FORCE_TILED | TORBI_B200_TILE_ROWS_MASK)) {
+    if (flags & (TORBI_B200_FORCE_TILED | TORBI_B200_TILE_ROWS_MASK | TORBI_B200_BANDED)) {
         if (!can_tile) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "tiled kernel does not support this shape");
         choice = kTiled;
     }
@@ -230,12 +230,16 @@ int decode_device(const float *observation, const int32_t *batch_frames,
     if (flags & TORBI_B200_FORCE_GENERIC) choice = kGeneric;
     const bool tiled = choice != kGeneric;               // kernels that honour frames_ready
     if (streamed) *streamed = tiled;
-    if (choice == kTiled && (flags & TORBI_B200_TILED_WS) && forward_tiled_ws_supported(a)) {
+    if (choice == kTiled && (flags & TORBI_B200_TILED_WS) && !(flags & TORBI_B200_BANDED) &&
+        forward_tiled_ws_supported(a)) {
         e = launch_forward_tiled_ws(a, stream);
         g_last_kernel = "forward_tiled_ws";
     } else if (choice == kTiled) {
         e = launch_forward_tiled(a, stream);
-        g_last_kernel = a.tile_rows == 64 ? "forward_tiled" : a.tile_rows == 32 ? "forward_tiled_32" : "forward_tiled_16";
+        if (flags & TORBI_B200_BANDED)
+            g_last_kernel = a.tile_rows == 64 ? "forward_tiled_banded" : a.tile_rows == 32 ? "forward_tiled_banded_32" : "forward_tiled_banded_16";
+        else
+            g_last_kernel = a.tile_rows == 64 ? "forward_tiled" : a.tile_rows == 32 ? "forward_tiled_32" : "forward_tiled_16";
     } else if (choice == kWide) {
         e = launch_forward_wide(a, stream);
         g_last_kernel = "forward_wide";

@@ -47,7 +47,7 @@ constexpr int stage_floats(int M) { return (tile_rows(M) + TN) * LDS_; }
 constexpr size_t smem_bytes(int M) {
     return sizeof(float) * (NSTAGE * stage_floats(M) + 2 * tile_rows(M) * TN)  // ring + emission/score + max tiles
            + sizeof(uint16_t) * tile_rows(M) * TN                              // winning chunk -> backpointer tile
-           + sizeof(int) * 2 * tile_rows(M);                                   // per-slot item id and length
+           + sizeof(int) * 4 * tile_rows(M);                                   // per-slot item id, length; banded: outside max / index
 }
 static_assert(smem_bytes(4) <= 227 * 1024, "shared memory budget");
 constexpr int kLoaders = 240;                 // 24 float4 columns x 10 rows per pass
@@ -114,6 +114,8 @@ struct TiledParams {
     int32_t *final_state;       // (B,)
     unsigned *sync;             // per group: barrier counter (+0) and current batch (+1); queue head at [0] of the last line
     const int32_t *frames_ready;  // frames of `observation` copied in so far, or null
+    const unsigned *band;         // banded mode: per destination tile S - first / last+1 source differing from `outside`
+    const float *outside;         // banded mode: the value every transition entry outside the windows has
     int64_t T;
     int S, LDP, NJT, NG, num_batches;
 };
@@ -170,10 +172,11 @@ __device__ __forceinline__ void load_stage(float *stage, const float *gA, const 
 // per lane group (all shared-memory reads, then all global loads, then the
 // compares -- nothing in a batch waits on an earlier output's store).
 // bp_tile holds the winning chunk on entry and the source index on exit.
-template <int TM, bool kFullTile>
+template <int TM, bool kFullTile, bool kBanded>
 __device__ __forceinline__ void rescan_tile(const float *best_tile, uint16_t *bp_tile,
                                             const int *slot_frames, const float *P_rows,
-                                            const float *A_rows, int LDP, int cols_valid, int S, int t) {
+                                            const float *A_rows, int LDP, int cols_valid, int S, int t,
+                                            const float *out_v, const int *out_i) {
     constexpr int kBatch = 20;
     constexpr int kRowsPerWarp = TM / (kThreads / kWarp);
     const int lane = threadIdx.x % kWarp, warp = threadIdx.x / kWarp;
@@ -216,6 +219,12 @@ __device__ __forceinline__ void rescan_tile(const float *best_tile, uint16_t *bp
                 key = min(key, __shfl_xor_sync(kFullMask, key, 4));
                 // (key == 64 only for NaN input, outside the parity contract)
                 k0[u] = min(k0[u] + (int)key, S - 1);
+                if (kBanded) {
+                    // sources outside the tile's window: larger value wins, equal values keep the lower index
+                    const float ov = out_v[r];
+                    const int oi = out_i[r];
+                    if (ov > best[u] || (ov == best[u] && oi < k0[u])) k0[u] = oi;
+                }
             }
             __syncwarp();       // every lane has read its chunk ids before they are overwritten
 #pragma unroll
@@ -227,7 +236,7 @@ __device__ __forceinline__ void rescan_tile(const float *best_tile, uint16_t *bp
     }
 }
 
-template <int M, uint32_t kFlags>
+template <int M, uint32_t kFlags, bool kBanded>
 __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledParams p) {
     constexpr int TM = tile_rows(M);
     constexpr int kStageFloats = stage_floats(M);
@@ -238,6 +247,8 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
     uint16_t *bp_tile = reinterpret_cast<uint16_t *>(best_tile + TM * TN);  // [TM][TN] chunk, then index
     int *slot_item = reinterpret_cast<int *>(bp_tile + TM * TN);       // [TM]
     int *slot_frames = slot_item + TM;                                 // [TM]
+    float *out_v = reinterpret_cast<float *>(slot_frames + TM);        // [TM] banded: max over sources outside the window
+    int *out_i = reinterpret_cast<int *>(out_v + TM);                  // [TM]          and its lowest index
     __shared__ int ready_shared;
     int ready = p.frames_ready ? 0 : 0x7fffffff;    // frames of `observation` known to be in HBM
     // the host entry copies the batch in T-chunks while this kernel runs: block
@@ -267,13 +278,26 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
     const int r_base = wb * (LANES_B * M) + lane_b;     // rows r_base + 8*i
     const int c_base = wj * (LANES_J * N) + lane_j;     // cols c_base + 4*c
     const int S = p.S, LDP = p.LDP;
-    const int nstages = LDP / KS;
+    // Pipeline stages this CTA runs per step.  Dense: all of them.  Banded: only the window
+    // outside which every transition entry of this destination tile equals *p.outside (the
+    // device-side analysis, analyze_band_kernel, guarantees it for any matrix).
+    int s_lo = 0, s_hi = LDP / KS;
+    float outside = 0.f;
+    if (kBanded) {
+        const int lo = S - (int)p.band[jt], hi = (int)p.band[p.NJT + jt];
+        s_lo = lo / KS;
+        s_hi = (hi + KS - 1) / KS;
+        if (lo >= hi) s_lo = s_hi = 0;
+        outside = *p.outside;
+    }
+    const int nstages = s_hi - s_lo;
+    const int k_lo = s_lo * KS, k_hi = min(s_hi * KS, S);
     const bool obs_vec = (S % 4) == 0 && (reinterpret_cast<uintptr_t>(p.observation) & 15) == 0;
     const bool bp_vec = (S % 8) == 0;
     // loader mapping (see load_stage)
     const int ld_c4 = tid % (KS / 4), ld_r0 = tid / (KS / 4);
     const int ld_smem = ld_r0 * LDS_ + ld_c4 * 4;
-    const float *ld_A = p.transition + (int64_t)(j0 + ld_r0) * LDP + ld_c4 * 4;
+    const float *ld_A = p.transition + (int64_t)(j0 + ld_r0) * LDP + ld_c4 * 4 + k_lo;
     const int64_t ld_stride10 = (int64_t)10 * LDP;
 
     unsigned *queue_head = p.sync + p.NG * 32;       // batches are handed out longest first
@@ -342,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                         tile[idx] = __ldg(p.observation + ((int64_t)item * p.T + t) * S + j0 + c);
                 }
             }
-            load_stage_A<TM>(ring + ld_smem, ld_A, ld_stride10);
+            if (nstages > 0) load_stage_A<TM>(ring + ld_smem, ld_A, ld_stride10);
             if (nstages > 1) load_stage_A<TM>(ring + kStageFloats + ld_smem, ld_A + KS, ld_stride10);
         };
         if (batch_frames > 1) prefetch_step(1);
@@ -355,14 +379,45 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             const float *P_cur = p.score0 + buf * p.score_stride;
             float *P_new = p.score0 + buf_new * p.score_stride;
             buf = buf_new;
-            const float *ld_P = P_cur + (row0 + ld_r0) * LDP + ld_c4 * 4;
+            const float *ld_P = P_cur + (row0 + ld_r0) * LDP + ld_c4 * 4 + k_lo;
 
             // the emission tile and the transition rows of stages 0 / 1 were prefetched before
             // the exchange wait (prefetch_step); only the score rows are left
-            load_stage_P<TM>(ring + ld_smem, ld_P, ld_stride10, ld_r0);
+            if (nstages > 0) load_stage_P<TM>(ring + ld_smem, ld_P, ld_stride10, ld_r0);
             cp_async_commit();
             if (nstages > 1) load_stage_P<TM>(ring + kStageFloats + ld_smem, ld_P + KS, ld_stride10, ld_r0);
             cp_async_commit();
+
+            if (kBanded) {
+                // sources outside the window: first-occurrence max of P[s] + outside, per sequence
+                // (the same single fp32 add the dense scan would do for these sources)
+                constexpr int kRowsPerWarp = TM / (kThreads / kWarp);
+                for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+                    const int r = warp * kRowsPerWarp + rr;
+                    float bv = -INFINITY;
+                    int bi = 0x7fffffff;
+                    if (t < slot_frames[r]) {
+                        const float *Prow = P_cur + (row0 + r) * LDP;
+                        for (int q = lane * 4; q < S; q += kWarp * 4) {
+                            if (q >= k_lo && q < k_hi) continue;            // window boundaries are multiples of 4
+                            const float4 pv = __ldcg(reinterpret_cast<const float4 *>(Prow + q));
+                            const float v0 = pv.x + outside, v1 = pv.y + outside, v2 = pv.z + outside, v3 = pv.w + outside;
+                            if (better(v0, q, bv, bi)) { bv = v0; bi = q; }
+                            if (q + 1 < S && v1 > bv) { bv = v1; bi = q + 1; }
+                            if (q + 2 < S && v2 > bv) { bv = v2; bi = q + 2; }
+                            if (q + 3 < S && v3 > bv) { bv = v3; bi = q + 3; }
+                        }
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) {
+                            const float ov = __shfl_xor_sync(kFullMask, bv, off);
+                            const int oi = __shfl_xor_sync(kFullMask, bi, off);
+                            if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+                        }
+                    }
+                    if (lane == 0) { out_v[r] = bv; out_i[r] = bi; }
+                }
+                __syncthreads();
+            }
 
             float cur[M][N];
             int bestc[M][N];
@@ -409,7 +464,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                                 acc[i][c] = fmaxf(fmaxf(fmaxf(fmaxf(a0, lo(v0)), hi(v0)), lo(v1)), hi(v1));
                             }
                     }
-                    const int chunk = s * (KS / KC) + ch;
+                    const int chunk = (s_lo + s) * (KS / KC) + ch;
 #pragma unroll
                     for (int i = 0; i < M; ++i)
 #pragma unroll
@@ -431,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                         const int col = c_base + c * LANES_J;
                         if (j0 + col < S) {
                             const float emit = convert_observation<kFlags>(tile[r * TN + col]);
-                            tile[r * TN + col] = emit + cur[i][c];
+                            tile[r * TN + col] = emit + (kBanded ? fmaxf(cur[i][c], out_v[r]) : cur[i][c]);
                             best_tile[r * TN + col] = cur[i][c];
                             bp_tile[r * TN + col] = (uint16_t)bestc[i][c];
                         }
@@ -465,11 +520,11 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             //      (a float4 of the chunk each), so every load is a coalesced 128-byte row.
 #ifndef TORBI_EXPERIMENT_SKIP_RESCAN      // timing experiments only: results are wrong without it
             if (j0 + TN <= S)
-                rescan_tile<TM, true>(best_tile, bp_tile, slot_frames, P_cur + row0 * LDP, p.transition + (int64_t)j0 * LDP,
-                                  LDP, S - j0, S, t);
+                rescan_tile<TM, true, kBanded>(best_tile, bp_tile, slot_frames, P_cur + row0 * LDP,
+                                               p.transition + (int64_t)j0 * LDP, LDP, S - j0, S, t, out_v, out_i);
             else
-                rescan_tile<TM, false>(best_tile, bp_tile, slot_frames, P_cur + row0 * LDP, p.transition + (int64_t)j0 * LDP,
-                                   LDP, S - j0, S, t);
+                rescan_tile<TM, false, kBanded>(best_tile, bp_tile, slot_frames, P_cur + row0 * LDP,
+                                                p.transition + (int64_t)j0 * LDP, LDP, S - j0, S, t, out_v, out_i);
 #endif
             __syncthreads();
 
@@ -528,6 +583,34 @@ __global__ void pad_transition_kernel(const float *__restrict__ src, float *__re
     }
 }
 
+// Banded mode, once per call: for every destination tile the range of sources whose
+// transition entry differs (bitwise) from the corner value A[0][S-1].  band[jt] = S - first,
+// band[NJT + jt] = last + 1 (both 0 for a tile that is constant), accumulated with atomicMax
+// on zero-initialised words.  Whatever the matrix looks like, entries outside the recorded
+// range equal `outside`, which is all the forward kernel relies on.
+__global__ void analyze_band_kernel(const float *__restrict__ transition, int S, int NJT,
+                                    unsigned *__restrict__ band, float *__restrict__ outside) {
+    const int lane = threadIdx.x % kWarp;
+    const int warps = gridDim.x * (blockDim.x / kWarp);
+    const unsigned c = __float_as_uint(transition[S - 1]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *outside = __uint_as_float(c);
+    for (int j = blockIdx.x * (blockDim.x / kWarp) + threadIdx.x / kWarp; j < S; j += warps) {
+        const float *row = transition + (int64_t)j * S;
+        int first = S, last = -1;
+        for (int s = lane; s < S; s += kWarp)
+            if (__float_as_uint(row[s]) != c) { first = min(first, s); last = max(last, s); }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            first = min(first, __shfl_xor_sync(kFullMask, first, off));
+            last = max(last, __shfl_xor_sync(kFullMask, last, off));
+        }
+        if (lane == 0 && last >= 0) {
+            atomicMax(band + j / TN, (unsigned)(S - first));
+            atomicMax(band + NJT + j / TN, (unsigned)(last + 1));
+        }
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_pad_transition(const ForwardArgs &a, cudaStream_t stream) {
@@ -544,7 +627,7 @@ bool forward_tiled_supported(const ForwardArgs &a) {
     return njt <= a.sm_count && a.ws.transition_pad != nullptr;
 }
 
-template <int M, uint32_t kFlags>
+template <int M, uint32_t kFlags, bool kBanded>
 static cudaError_t launch_tiled_t(const ForwardArgs &a, cudaStream_t stream) {
     constexpr int TM = tile_rows(M);
     TiledParams p{};
@@ -571,8 +654,19 @@ static cudaError_t launch_tiled_t(const ForwardArgs &a, cudaStream_t stream) {
 
     cudaError_t e = launch_pad_transition(a, stream);
     if (e != cudaSuccess) return e;
+    if (kBanded) {
+        // the analysis words live in the (zeroed) second half of the sync area
+        unsigned *band = a.ws.sync + kSyncWords / 2;
+        float *outside = reinterpret_cast<float *>(band + 2 * p.NJT);
+        if (2 * p.NJT + 1 > (int)kSyncWords / 2) return cudaErrorInvalidValue;
+        analyze_band_kernel<<<a.sm_count, 256, 0, stream>>>(a.transition, p.S, p.NJT, band, outside);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        p.band = band;
+        p.outside = outside;
+    }
 
-    auto kernel = forward_tiled_kernel<M, kFlags>;
+    auto kernel = forward_tiled_kernel<M, kFlags, kBanded>;
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(M));
     if (e != cudaSuccess) return e;
     void *args[] = {(void *)&p};
@@ -584,11 +678,12 @@ static cudaError_t launch_tiled_t(const ForwardArgs &a, cudaStream_t stream) {
 
 template <int M>
 static cudaError_t launch_tiled_m(const ForwardArgs &a, cudaStream_t stream) {
+    const bool banded = a.flags & TORBI_B200_BANDED;
     switch (a.flags & 3u) {
-        case 0: return launch_tiled_t<M, 0>(a, stream);
-        case 1: return launch_tiled_t<M, 1>(a, stream);
-        case 2: return launch_tiled_t<M, 2>(a, stream);
-        default: return launch_tiled_t<M, 3>(a, stream);
+        case 0: return banded ? launch_tiled_t<M, 0, true>(a, stream) : launch_tiled_t<M, 0, false>(a, stream);
+        case 1: return banded ? launch_tiled_t<M, 1, true>(a, stream) : launch_tiled_t<M, 1, false>(a, stream);
+        case 2: return banded ? launch_tiled_t<M, 2, true>(a, stream) : launch_tiled_t<M, 2, false>(a, stream);
+        default: return banded ? launch_tiled_t<M, 3, true>(a, stream) : launch_tiled_t<M, 3, false>(a, stream);
     }
 }
 
