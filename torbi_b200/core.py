@@ -12,6 +12,7 @@ Differences from the reference, all on purpose:
     `conversion='host'` reproduces the reference's CPU torch ops exactly instead.
 """
 import concurrent.futures
+import functools
 import math
 import os
 import queue
@@ -383,7 +384,8 @@ def from_files_to_files(
     if len(devices) == 1:
         from_dataloader(
             dataloader=torbi_b200.data.loader(
-                input_files, batch_sampler=size_bucketed_batches(sizes, torbi_b200.BATCH_SIZE)),
+                input_files, batch_sampler=size_bucketed_batches(sizes, torbi_b200.BATCH_SIZE),
+                collate_fn=_pinned_collate()),
             output_files=mapping,
             transition=transition,
             initial=initial,
@@ -403,7 +405,8 @@ def from_files_to_files(
             from_dataloader(
                 dataloader=torbi_b200.data.loader(
                     shard_files, batch_sampler=size_bucketed_batches(
-                        [sizes[i] for i in items], torbi_b200.BATCH_SIZE)),
+                        [sizes[i] for i in items], torbi_b200.BATCH_SIZE),
+                    collate_fn=_pinned_collate()),
                 output_files=mapping,
                 transition=transition,
                 initial=initial,
@@ -430,6 +433,13 @@ def from_files_to_files(
 ###############################################################################
 
 
+def _pinned_collate():
+    """collate() that assembles the batch directly in page-locked memory when a GPU is there
+    (in-process loaders only: worker processes hand tensors over through shared memory)."""
+    pin = torch.cuda.is_available() and torbi_b200.NUM_WORKERS == 0
+    return functools.partial(torbi_b200.data.collate, pin_memory=pin)
+
+
 def _prefetched(dataloader, depth):
     """Iterate `dataloader` on a background thread, `depth` batches ahead, with the
     padded observation pinned so its host->device copy runs at full PCIe rate."""
@@ -442,7 +452,7 @@ def _prefetched(dataloader, depth):
     def produce():
         try:
             for observation, batch_frames, batch_chunks, files in dataloader:
-                if torch.cuda.is_available():
+                if torch.cuda.is_available() and not observation.is_pinned():
                     observation = observation.pin_memory()
                 batches.put((observation, batch_frames, batch_chunks, files))
             batches.put(done)
