@@ -162,6 +162,18 @@ def test_banded_fast_path_is_exact(states, width, outside, oracle):
         assert np.array_equal(bits(posterior), bits(want_post))
 
 
+def test_very_wide_state_space(oracle):
+    """S = 20000: beyond the tiled kernel (250 destination tiles > 148 SMs); the selector
+    falls back to the wide kernel, and the generic kernel must agree."""
+    obs, frames, A, init = random_problem(5, 2, 4, 20000, ragged=False)
+    want = oracle.c_decode(obs, frames, A, init, exact_scan=False)
+    for flags in (0, _ffi.FORCE_GENERIC, _ffi.FORCE_WIDE):
+        indices, _ = gpu_decode(obs, frames, A, init, flags=flags)
+        assert np.array_equal(indices, want)
+    with pytest.raises(ValueError, match='tiled kernel does not support'):
+        gpu_decode(obs, frames, A, init, flags=_ffi.FORCE_TILED)
+
+
 def test_padding_is_never_read(oracle):
     # garbage (NaN) beyond batch_frames must not influence anything (SURVEY A1)
     obs, frames, A, init = random_problem(7, 6, 30, 200)
@@ -389,6 +401,15 @@ def test_file_drivers(tmp_path, oracle):
         x = torch.load(path).unsqueeze(0)
         want = oracle.ref_from_probabilities(x, None, torch.from_numpy(A), initial, True)
         assert np.array_equal(got.numpy(), want[0])
+
+    # several "GPUs" (the same one twice here): files sharded by size, one worker thread each
+    for out in outputs:
+        out.unlink()
+    torbi_b200.from_files_to_files(
+        files, outputs, tmp_path / 'transition.pt', tmp_path / 'initial.pt', log_probs=True, gpu=[0, 0])
+    for path, out, f in zip(files, outputs, lengths):
+        want = oracle.ref_from_probabilities(torch.load(path).unsqueeze(0), None, torch.from_numpy(A), initial, True)
+        assert np.array_equal(torch.load(out).numpy(), want[0])
 
     # from_file: transition logged WITHOUT tiny (core.py:247-250), shape (1, frames)
     got = torbi_b200.from_file(files[0], tmp_path / 'transition.pt', tmp_path / 'initial.pt',

@@ -391,30 +391,55 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             if (kBanded) {
                 // sources outside the window: first-occurrence max of P[s] + outside, per sequence
                 // (the same single fp32 add the dense scan would do for these sources)
+                // All rows of the warp advance together so their (independent) L2 loads overlap.
+                // Per lane and row: running max over the lane's ascending float4 groups and the FIRST
+                // group that strictly raised it; the index inside that group is resolved afterwards.
                 constexpr int kRowsPerWarp = TM / (kThreads / kWarp);
+                const float *Prow0 = P_cur + (row0 + warp * kRowsPerWarp) * LDP;
+                float bv[kRowsPerWarp];
+                int grp[kRowsPerWarp];
+#pragma unroll
+                for (int rr = 0; rr < kRowsPerWarp; ++rr) { bv[rr] = -INFINITY; grp[rr] = -1; }
+#pragma unroll 2
+                for (int q = lane * 4; q < S; q += kWarp * 4) {
+                    if (q >= k_lo && q < k_hi) continue;                // window boundaries are multiples of 4
+                    float4 pv[kRowsPerWarp];
+#pragma unroll
+                    for (int rr = 0; rr < kRowsPerWarp; ++rr)
+                        pv[rr] = __ldcg(reinterpret_cast<const float4 *>(Prow0 + (int64_t)rr * LDP + q));
+#pragma unroll
+                    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+                        if (q + 3 >= S) {                                // ragged tail: padding never competes
+                            if (q + 1 >= S) pv[rr].y = -INFINITY;
+                            if (q + 2 >= S) pv[rr].z = -INFINITY;
+                            pv[rr].w = -INFINITY;
+                        }
+                        const float m = fmaxf(fmaxf(pv[rr].x + outside, pv[rr].y + outside),
+                                              fmaxf(pv[rr].z + outside, pv[rr].w + outside));
+                        if (m > bv[rr] || grp[rr] < 0) { bv[rr] = m; grp[rr] = q; }
+                    }
+                }
+#pragma unroll
                 for (int rr = 0; rr < kRowsPerWarp; ++rr) {
                     const int r = warp * kRowsPerWarp + rr;
-                    float bv = -INFINITY;
+                    float v = bv[rr];
                     int bi = 0x7fffffff;
-                    if (t < slot_frames[r]) {
-                        const float *Prow = P_cur + (row0 + r) * LDP;
-                        for (int q = lane * 4; q < S; q += kWarp * 4) {
-                            if (q >= k_lo && q < k_hi) continue;            // window boundaries are multiples of 4
-                            const float4 pv = __ldcg(reinterpret_cast<const float4 *>(Prow + q));
-                            const float v0 = pv.x + outside, v1 = pv.y + outside, v2 = pv.z + outside, v3 = pv.w + outside;
-                            if (better(v0, q, bv, bi)) { bv = v0; bi = q; }
-                            if (q + 1 < S && v1 > bv) { bv = v1; bi = q + 1; }
-                            if (q + 2 < S && v2 > bv) { bv = v2; bi = q + 2; }
-                            if (q + 3 < S && v3 > bv) { bv = v3; bi = q + 3; }
-                        }
-#pragma unroll
-                        for (int off = 16; off > 0; off >>= 1) {
-                            const float ov = __shfl_xor_sync(kFullMask, bv, off);
-                            const int oi = __shfl_xor_sync(kFullMask, bi, off);
-                            if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-                        }
+                    if (grp[rr] >= 0) {
+                        const int g = grp[rr];
+                        const float4 pv = __ldcg(reinterpret_cast<const float4 *>(Prow0 + (int64_t)rr * LDP + g));
+                        bi = g + 3;
+                        if (g + 2 < S && pv.z + outside == v) bi = g + 2;
+                        if (g + 1 < S && pv.y + outside == v) bi = g + 1;
+                        if (pv.x + outside == v) bi = g;
                     }
-                    if (lane == 0) { out_v[r] = bv; out_i[r] = bi; }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const float ov = __shfl_xor_sync(kFullMask, v, off);
+                        const int oi = __shfl_xor_sync(kFullMask, bi, off);
+                        if (better(ov, oi, v, bi)) { v = ov; bi = oi; }
+                    }
+                    // (rows of finished / empty slots are scanned too: their result is never used)
+                    if (lane == 0) { out_v[r] = v; out_i[r] = bi; }
                 }
                 __syncthreads();
             }
