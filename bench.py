@@ -50,6 +50,8 @@ def parse_args():
     parser.add_argument('--frames', type=int, default=2000)
     parser.add_argument('--states', type=int, default=1440)
     parser.add_argument('--no-e2e', action='store_true')
+    parser.add_argument('--cpu-seconds', type=float, default=None,
+                        help='CPU work per reference step / cpu_baseline sample (default: sized automatically)')
     parser.add_argument('--no-cpu-baseline', action='store_true')
     parser.add_argument('--kernel', default='auto', choices=['auto', 'generic', 'tiled', 'wide'])
     parser.add_argument('--tile-rows', type=int, default=0, choices=[0, 16, 32, 64])
@@ -201,7 +203,7 @@ def bench_reference(args):
     if rank != 0:
         return
     budget = 150.0 / max(1, args.steps + args.warmup)
-    step, timesteps, kind, cores, sample = cpu_sample(args, min(20.0, budget))
+    step, timesteps, kind, cores, sample = cpu_sample(args, args.cpu_seconds or min(20.0, budget))
     for _ in range(args.warmup):
         step()
     elapsed = sum(step() for _ in range(args.steps))
@@ -367,7 +369,7 @@ def bench_graft(args):
             'checksum': checksum,
         }
         if world == 1 and not args.no_cpu_baseline:
-            step_cpu, timesteps, kind, cores, sample = cpu_sample(args, 15.0)
+            step_cpu, timesteps, kind, cores, sample = cpu_sample(args, args.cpu_seconds or 15.0)
             seconds = step_cpu()
             line['cpu_baseline'] = {'value': timesteps / seconds, 'unit': UNIT, 'cores': cores,
                                     'kind': kind, 'sample': sample}
