@@ -9,8 +9,9 @@
 //     group owns the TN = 80 destination states [jt*TN, jt*TN+TN) for all T steps;
 //   * per step every CTA streams its A slice [TN x S] and the batch's previous
 //     scores P[TM x S] from L2 through a 3-stage cp.async ring (96 source states
-//     per stage), so A is re-read once per 64 sequences instead of once per
-//     sequence as in the reference kernel (viterbi.cu:91,97);
+//     per stage) synchronised by mbarriers (full: copies landed, empty: warps done;
+//     no CTA-wide barrier per stage), so A is re-read once per 64 sequences instead
+//     of once per sequence as in the reference kernel (viterbi.cu:91,97);
 //   * the new scores are published to global memory (L2) and the group meets at
 //     a counter barrier; groups never wait for each other.
 //
@@ -25,6 +26,7 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "sync.cuh"
 
 namespace torbi_b200 {
 
@@ -47,13 +49,12 @@ constexpr int stage_floats(int M) { return (tile_rows(M) + TN) * LDS_; }
 constexpr size_t smem_bytes(int M) {
     return sizeof(float) * (NSTAGE * stage_floats(M) + 2 * tile_rows(M) * TN)  // ring + emission/score + max tiles
            + sizeof(uint16_t) * tile_rows(M) * TN                              // winning chunk -> backpointer tile
-           + sizeof(int) * 4 * tile_rows(M);                                   // per-slot item id, length; banded: outside max / index
+           + sizeof(int) * 4 * tile_rows(M)                                    // per-slot item id, length; banded: outside max / index
+           + sizeof(u64) * 2 * NSTAGE;                                         // full / empty mbarrier per ring slot
 }
 static_assert(smem_bytes(4) <= 227 * 1024, "shared memory budget");
 constexpr int kLoaders = 240;                 // 24 float4 columns x 10 rows per pass
 static_assert(KS / 4 == 24 && TN % 10 == 0, "loader mapping");
-
-typedef unsigned long long u64;
 
 __device__ __forceinline__ u64 add2(u64 a, u64 b) {     // two fp32 adds (FADD2), IEEE rn
     u64 d;
@@ -249,6 +250,20 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
     int *slot_frames = slot_item + TM;                                 // [TM]
     float *out_v = reinterpret_cast<float *>(slot_frames + TM);        // [TM] banded: max over sources outside the window
     int *out_i = reinterpret_cast<int *>(out_v + TM);                  // [TM]          and its lowest index
+    // Ring synchronisation without CTA-wide barriers: full[slot] collects one arrival per thread
+    // once its async copies for the stage have landed; empty[slot] one per warp once it has
+    // finished reading the stage.  Warps may drift apart by up to a stage.
+    u64 *full_bar = reinterpret_cast<u64 *>(out_i + TM);               // [NSTAGE]
+    u64 *empty_bar = full_bar + NSTAGE;                                // [NSTAGE]
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < NSTAGE; ++k) {
+            mbar_init(full_bar + k, kThreads);
+            mbar_init(empty_bar + k, kThreads / kWarp);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    unsigned stage_counter = 0;      // pipeline stages consumed so far by this thread (slot = counter % NSTAGE)
     __shared__ int ready_shared;
     int ready = p.frames_ready ? 0 : 0x7fffffff;    // frames of `observation` known to be in HBM
     // the host entry copies the batch in T-chunks while this kernel runs: block
@@ -366,8 +381,10 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                         tile[idx] = __ldg(p.observation + ((int64_t)item * p.T + t) * S + j0 + c);
                 }
             }
-            if (nstages > 0) load_stage_A<TM>(ring + ld_smem, ld_A, ld_stride10);
-            if (nstages > 1) load_stage_A<TM>(ring + kStageFloats + ld_smem, ld_A + KS, ld_stride10);
+            // (stage_counter already points at the first stage of step t: the previous step is done)
+            if (nstages > 0) load_stage_A<TM>(ring + (stage_counter % NSTAGE) * kStageFloats + ld_smem, ld_A, ld_stride10);
+            if (nstages > 1)
+                load_stage_A<TM>(ring + ((stage_counter + 1) % NSTAGE) * kStageFloats + ld_smem, ld_A + KS, ld_stride10);
         };
         if (batch_frames > 1) prefetch_step(1);
 
@@ -383,10 +400,17 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
 
             // the emission tile and the transition rows of stages 0 / 1 were prefetched before
             // the exchange wait (prefetch_step); only the score rows are left
-            if (nstages > 0) load_stage_P<TM>(ring + ld_smem, ld_P, ld_stride10, ld_r0);
-            cp_async_commit();
-            if (nstages > 1) load_stage_P<TM>(ring + kStageFloats + ld_smem, ld_P + KS, ld_stride10, ld_r0);
-            cp_async_commit();
+            {
+                const unsigned slot0 = stage_counter % NSTAGE, slot1 = (stage_counter + 1) % NSTAGE;
+                if (nstages > 0) {
+                    load_stage_P<TM>(ring + slot0 * kStageFloats + ld_smem, ld_P, ld_stride10, ld_r0);
+                    cp_async_arrive(full_bar + slot0);
+                }
+                if (nstages > 1) {
+                    load_stage_P<TM>(ring + slot1 * kStageFloats + ld_smem, ld_P + KS, ld_stride10, ld_r0);
+                    cp_async_arrive(full_bar + slot1);
+                }
+            }
 
             if (kBanded) {
                 // sources outside the window: first-occurrence max of P[s] + outside, per sequence
@@ -451,23 +475,27 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
 #pragma unroll
                 for (int c = 0; c < N; ++c) { cur[i][c] = -INFINITY; bestc[i][c] = 0; }
 
-            for (int s = 0; s < nstages; ++s) {
-                cp_async_wait<1>();
-                __syncthreads();            // stage s landed; everyone is done with stage s-1
+            for (int s = 0; s < nstages; ++s, ++stage_counter) {
+                const unsigned slot = stage_counter % NSTAGE;
+                // every thread's copies for this stage have landed
+                mbar_wait(full_bar + slot, (stage_counter / NSTAGE) & 1);
                 const bool refill = s + 2 < nstages;
-                float *refill_dst = ring + ((s + 2) % NSTAGE) * kStageFloats + ld_smem;
+                const unsigned rslot = (stage_counter + 2) % NSTAGE;          // the previous stage's slot
+                float *refill_dst = ring + rslot * kStageFloats + ld_smem;
                 const float *refill_A = ld_A + (s + 2) * KS, *refill_P = ld_P + (s + 2) * KS;
 
-                const float *Ps = ring + (s % NSTAGE) * kStageFloats + r_base * LDS_;
-                const float *As = ring + (s % NSTAGE) * kStageFloats + (TM + c_base) * LDS_;
+                const float *Ps = ring + slot * kStageFloats + r_base * LDS_;
+                const float *As = ring + slot * kStageFloats + (TM + c_base) * LDS_;
 #pragma unroll
                 for (int ch = 0; ch < KS / KC; ++ch) {
-                    if (refill) {
-                        if (ch == 0) load_stage_part<TM, 0>(refill_dst, refill_A, refill_P, ld_stride10, ld_r0);
-                        if (ch == 1) load_stage_part<TM, 1>(refill_dst, refill_A, refill_P, ld_stride10, ld_r0);
-                        if (ch == 2) load_stage_part<TM, 2>(refill_dst, refill_A, refill_P, ld_stride10, ld_r0);
+                    if (refill && ch == 1) {
+                        // Refill the slot the previous stage used, one chunk into this stage: by now every
+                        // warp has (almost surely) released it, so the wait does not couple the warps.
+                        const unsigned uses = (stage_counter + 2) / NSTAGE;     // earlier uses of that slot
+                        if (uses > 0) mbar_wait(empty_bar + rslot, (uses - 1) & 1);
+                        load_stage<TM>(refill_dst, refill_A, refill_P, ld_stride10, ld_r0);
+                        cp_async_arrive(full_bar + rslot);
                     }
-                    if (ch == KS / KC - 1) cp_async_commit();
                     float acc[M][N];
 #pragma unroll
                     for (int k = 0; k < KC; k += 4) {
@@ -498,8 +526,16 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                             cur[i][c] = acc[i][c];
                         }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_bar + slot);          // this warp is done with the slot
             }
-            cp_async_wait<0>();     // the emission tile (first group) is long since in
+            // The emission tile was copied with the step's first stage, whose full-barrier every thread
+            // has passed.  Without any stage (banded, empty window) or with plain stores (unaligned
+            // observations) a CTA barrier makes the other threads' tile writes visible instead.
+            if (nstages == 0 || !obs_vec) {
+                cp_async_wait<0>();
+                __syncthreads();
+            }
 
             // ---- new scores: obs[t][j] + max  (viterbi.cpp:102); keep max and winning chunk ----
 #pragma unroll
@@ -713,7 +749,7 @@ static cudaError_t launch_tiled_m(const ForwardArgs &a, cudaStream_t stream) {
 }
 
 // Relative cost of one timestep of a TM-row batch (measured on the B200, S = 1440).
-static double step_cost(int tm) { return tm == 64 ? 1.0 : tm == 32 ? 0.60 : 0.51; }
+static double step_cost(int tm) { return tm == 64 ? 1.0 : tm == 32 ? 0.57 : 0.46; }
 
 // Batch height for this call: simulate longest-first list scheduling of the
 // length-sorted batches over the CTA groups for TM = 64 / 32 / 16 and take the
@@ -735,8 +771,8 @@ int tiled_choose_rows(const int32_t *frames_sorted, int64_t B, int64_t S, int sm
         const double makespan = *std::max_element(load.begin(), load.end());
         if (makespan < best * 0.97) { best = makespan; best_tm = tm; }   // prefer the taller tile on near-ties
     }
-    // one step of a 64-row batch takes 87.5 us at S = 1440 and scales with the K loop
-    if (seconds) *seconds = best * 87.5e-6 * (double)tiled_ldp(S) / 1440.0;
+    // one step of a 64-row batch takes 86 us at S = 1440 (49 / 40 us for 32 / 16 rows) and scales with the K loop
+    if (seconds) *seconds = best * 86.0e-6 * (double)tiled_ldp(S) / 1440.0;
     return best_tm;
 }
 
