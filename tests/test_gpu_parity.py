@@ -162,6 +162,15 @@ def test_banded_fast_path_is_exact(states, width, outside, oracle):
         assert np.array_equal(bits(posterior), bits(want_post))
 
 
+@pytest.mark.parametrize('kernel', ['tiled16', 'banded16', 'auto'])
+def test_many_small_batches_use_every_cta_group(kernel, oracle):
+    """Few states, many sequences: one CTA per group, 148 groups, every scheduling word in use."""
+    obs, frames, A, init = random_problem(9, 3000, 3, 48)
+    want = oracle.c_decode(obs, frames, A, init)
+    indices, _ = gpu_decode(obs, frames, A, init, flags=KERNELS[kernel])
+    assert np.array_equal(indices, want)
+
+
 def test_very_wide_state_space(oracle):
     """S = 20000: beyond the tiled kernel (250 destination tiles > 148 SMs); the selector
     falls back to the wide kernel, and the generic kernel must agree."""

@@ -53,7 +53,10 @@ struct Workspace {
     size_t bytes;
 };
 
-constexpr size_t kSyncWords = 4096;
+// scheduling words, zeroed per call: [0, 6144) one 128-byte line per CTA group (<= 148 groups + queue
+// head), [6144, 8192) the banded-mode analysis (2 words per destination tile + the outside value)
+constexpr size_t kSyncWords = 8192;
+constexpr size_t kBandWordOffset = 6144;
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

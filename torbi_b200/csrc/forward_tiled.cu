@@ -711,15 +711,15 @@ static cudaError_t launch_tiled_t(const ForwardArgs &a, cudaStream_t stream) {
     p.NJT = SJ / TN;
     p.num_batches = (int)((a.B + TM - 1) / TM);
     p.NG = std::min(a.sm_count / p.NJT, p.num_batches);
-    if ((p.NG + 1) * 32 > (int)kSyncWords) return cudaErrorInvalidValue;
+    if ((p.NG + 1) * 32 > (int)kBandWordOffset) return cudaErrorInvalidValue;
 
     cudaError_t e = launch_pad_transition(a, stream);
     if (e != cudaSuccess) return e;
     if (kBanded) {
-        // the analysis words live in the (zeroed) second half of the sync area
-        unsigned *band = a.ws.sync + kSyncWords / 2;
+        // the analysis words live in the (zeroed) tail of the sync area
+        unsigned *band = a.ws.sync + kBandWordOffset;
         float *outside = reinterpret_cast<float *>(band + 2 * p.NJT);
-        if (2 * p.NJT + 1 > (int)kSyncWords / 2) return cudaErrorInvalidValue;
+        if (2 * p.NJT + 1 > (int)(kSyncWords - kBandWordOffset)) return cudaErrorInvalidValue;
         analyze_band_kernel<<<a.sm_count, 256, 0, stream>>>(a.transition, p.S, p.NJT, band, outside);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;

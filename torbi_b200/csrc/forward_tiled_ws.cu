@@ -550,7 +550,7 @@ static cudaError_t launch_ws_t(const ForwardArgs &a, cudaStream_t stream) {
     p.NJT = (int)(padded_dests(a.S) / TN);
     p.num_batches = (int)((a.B + TM - 1) / TM);
     p.NG = std::min(a.sm_count / p.NJT, p.num_batches);
-    if ((p.NG + 1) * 32 > (int)kSyncWords) return cudaErrorInvalidValue;
+    if ((p.NG + 1) * 32 > (int)kBandWordOffset) return cudaErrorInvalidValue;
     cudaError_t e = launch_pad_transition(a, stream);
     if (e != cudaSuccess) return e;
     auto kernel = forward_tiled_ws_kernel<kFlags>;
