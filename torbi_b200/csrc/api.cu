@@ -257,7 +257,8 @@ int decode_device(const float *observation, const int32_t *batch_frames,
         cudaEventRecord(g_timing.ev[2], stream);
         g_timing.valid = true;
     }
-    g_launches += tiled ? 3 : 2;      // (pad_transition +) forward + backtrace
+    // kernels enqueued: (pad_transition + [analyze_band] +) forward + backtrace
+    g_launches += tiled ? (choice == kTiled && (flags & TORBI_B200_BANDED) ? 4 : 3) : 2;
     return TORBI_B200_OK;
 }
 
