@@ -277,6 +277,19 @@ def test_dispatcher_op_on_gpu(oracle):
     assert np.array_equal(got.cpu().numpy(), oracle.c_decode(obs, frames, A, init))
 
 
+def test_uniform_default_transition_through_the_banded_path(oracle):
+    """transition=None on a big enough batch: the all-constant default matrix has an empty
+    window in every tile, so the whole step is the outside scan -- still the reference's answer
+    (lots of exact ties: every destination sees the same candidates)."""
+    rng = np.random.default_rng(77)
+    obs = torch.from_numpy(cases.log_softmax(rng.standard_normal((40, 9, 512))))
+    frames = torch.from_numpy(rng.integers(1, 10, size=40).astype(np.int32))
+    got = torbi_b200.from_probabilities(obs, frames, log_probs=True, gpu=0)
+    assert _ffi.library().torbi_b200_last_kernel().decode().startswith('forward_tiled_banded')
+    want = oracle.ref_from_probabilities(obs, frames, None, None, True)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
 def test_errors_on_gpu():
     obs = torch.rand(2, 4, 5, device='cuda:0')
     A, init = torch.rand(5, 5, device='cuda:0'), torch.rand(5, device='cuda:0')

@@ -195,6 +195,16 @@ def test_evaluate_transition_and_rpa():
     assert result == {'rpa': {'0': 0.5, '1': 0.75, '2': 1.0}}
 
 
+def test_banded_hint_detects_the_pitch_transition():
+    import cases
+    from torbi_b200.core import _is_banded
+    assert _is_banded(torch.from_numpy(cases.log_triangular_transition(1440)))
+    assert not _is_banded(torch.log_softmax(torch.randn(1440, 1440), dim=-1))
+    assert not _is_banded(torch.from_numpy(cases.log_triangular_transition(96, 6.5)))   # too small to matter
+    dense_default = torch.full((512, 512), -6.2)
+    assert _is_banded(dense_default)      # all-constant: the window is empty, the fast path is exact and cheapest
+
+
 def test_product_never_imports_the_oracle():
     # the oracle is test infrastructure: nothing under torbi_b200/ may reference it
     for path in (ROOT / 'torbi_b200').rglob('*'):

@@ -161,14 +161,14 @@ def _from_probabilities_one(observation, batch_frames, transition, initial, log_
     if transition is None:
         transition = torch.full(
             (states, states), math.log(1. / states), dtype=torch.float32, device=device)
-        banded = False if banded is None else banded
     else:
         if not log_probs:
             transition = torch.log(transition)
         transition = transition.to(dtype=torch.float32)
-        if banded is None:
-            banded = _is_banded(transition)
-        transition = transition.to(device=device)
+    if banded is None:
+        # small batches are better served by the wide kernel, which the flag would rule out
+        banded = batch >= 32 and _is_banded(transition)
+    transition = transition.to(device=device)
 
     observation, flags = _prepare_observation(observation, log_probs, device, mode)
     if banded:

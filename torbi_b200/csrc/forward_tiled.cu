@@ -362,7 +362,8 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
 
         // Everything step `t` needs that does not depend on the other CTAs: its emission tile
         // (raw; converted when consumed) and the transition rows of pipeline stages 0 and 1.
-        // Issued without a commit: they join the step's first cp.async group.
+        // Their completion is covered by the full-barrier arrival of the step's first stage
+        // (cp.async.mbarrier.arrive tracks every earlier cp.async of the thread).
         auto prefetch_step = [&](int t) {
             wait_for_frame(t);
             if (obs_vec) {
