@@ -70,6 +70,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target)
 
 template <int BC, uint32_t kFlags>
 __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const WideParams p) {
+    constexpr int BW = BC < 4 ? BC : 4;                  // sequences scanned together by one warp
     extern __shared__ __align__(16) float smem[];
     const int S = p.S, LDP = p.LDP, R = p.R;
     float *Ps = smem;                                    // [BC][LDP] previous scores
@@ -146,40 +147,52 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
                 reinterpret_cast<float4 *>(Ps)[idx] = __ldcg(reinterpret_cast<const float4 *>(P_cur) + idx);
             __syncthreads();
 
-            for (int j = j_begin + warp; j < j_end; j += kWideWarps) {
+            // Work items = (destination row, sub-group of BW sequences), dealt round-robin to the
+            // warps: with R = 10 rows and 16 sequences that is 40 items for 16 warps instead of
+            // 10 busy warps scanning 16 sequences each.
+            const int subgroups = (nb + BW - 1) / BW;
+            const int items = (j_end - j_begin) * subgroups;
+            for (int item_id = warp; item_id < items; item_id += kWideWarps) {
+                const int j = j_begin + item_id / subgroups;
+                const int b0 = (item_id % subgroups) * BW;
+                const int nbw = min(BW, nb - b0);                 // sequences of this item
                 // emissions (and carried scores of finished sequences) fetched early by lane b
                 float emit = 0.f;
-                if (lane < nb) {
-                    const int item = slot_item[lane];
-                    emit = t < slot_frames[lane]
+                if (lane < nbw) {
+                    const int item = slot_item[b0 + lane];
+                    emit = t < slot_frames[b0 + lane]
                         ? convert_observation<kFlags>(__ldg(p.observation + ((int64_t)item * p.T + t) * S + j))
-                        : __ldcg(P_cur + (int64_t)lane * LDP + j);
+                        : __ldcg(P_cur + (int64_t)(b0 + lane) * LDP + j);
                 }
-                float best[BC];
-                int grp[BC];
+                float best[BW];
+                int grp[BW];
+                const float *prow[BW];
                 const bool has_groups = lane < LDP / 4;          // S <= 96: lanes 24..31 own no source state
 #pragma unroll
-                for (int b = 0; b < BC; ++b) { best[b] = -INFINITY; grp[b] = has_groups ? lane : 0; }
-                int arg_b[BC];
+                for (int b = 0; b < BW; ++b) {
+                    best[b] = -INFINITY;
+                    grp[b] = has_groups ? lane : 0;
+                    // slots past the item's last sequence re-read its row: no branch between the loads
+                    prow[b] = Ps + (b0 + (b < nbw ? b : nbw - 1)) * LDP;
+                }
+                int arg_b[BW];
                 // the scan, parametrised on where the transition row lives: resident rows are
-                // read with LDS, the rest of the slice streams from L2 through the read-only path
+                // read with LDS, the rest of the slice streams from L2
                 auto scan_row = [&](auto load_a) {
                     for (int q = lane; q < LDP / 4; q += kWarp) {
                         const float4 a = load_a(q);
 #pragma unroll
-                        for (int b = 0; b < BC; ++b) {
-                            if (b < nb) {
-                                const float4 pv = reinterpret_cast<const float4 *>(Ps + b * LDP)[q];
-                                const float m = fmaxf(fmaxf(pv.x + a.x, pv.y + a.y), fmaxf(pv.z + a.z, pv.w + a.w));
-                                if (m > best[b]) { best[b] = m; grp[b] = q; }     // first group reaching the max
-                            }
+                        for (int b = 0; b < BW; ++b) {
+                            const float4 pv = reinterpret_cast<const float4 *>(prow[b])[q];
+                            const float m = fmaxf(fmaxf(pv.x + a.x, pv.y + a.y), fmaxf(pv.z + a.z, pv.w + a.w));
+                            if (m > best[b]) { best[b] = m; grp[b] = q; }         // first group reaching the max
                         }
                     }
 #pragma unroll
-                    for (int b = 0; b < BC; ++b) {
+                    for (int b = 0; b < BW; ++b) {
                         // lowest index inside the lane's winning group
                         const float4 a = load_a(grp[b]);
-                        const float4 pv = reinterpret_cast<const float4 *>(Ps + (b < nb ? b : 0) * LDP)[grp[b]];
+                        const float4 pv = reinterpret_cast<const float4 *>(prow[b])[grp[b]];
                         int arg = 4 * grp[b] + 3;
                         if (pv.z + a.z == best[b]) arg = 4 * grp[b] + 2;
                         if (pv.y + a.y == best[b]) arg = 4 * grp[b] + 1;
@@ -195,8 +208,8 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
                     scan_row([&](int q) { return arow[q]; });   // plain LDG: measured 2x faster here than the .nc path
                 }
 #pragma unroll
-                for (int b = 0; b < BC; ++b) {
-                    if (b >= nb) continue;
+                for (int b = 0; b < BW; ++b) {
+                    if (b >= nbw) continue;
                     // ... then across lanes
                     int arg = arg_b[b];
                     if (!has_groups) arg = 0x7fffffff;            // (-inf, INT_MAX) never wins a tie
@@ -209,10 +222,11 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
                     }
                     const float e = __shfl_sync(kFullMask, emit, b);
                     if (lane == 0) {
-                        const bool live = t < slot_frames[b];
-                        P_new[(int64_t)b * LDP + j] = live ? e + v : e;          // viterbi.cpp:102 / carried
+                        const int bb = b0 + b;
+                        const bool live = t < slot_frames[bb];
+                        P_new[(int64_t)bb * LDP + j] = live ? e + v : e;         // viterbi.cpp:102 / carried
                         if (live)
-                            p.backptr[((int64_t)slot_item[b] * p.T + t) * S + j] = (uint16_t)min(arg, S - 1);
+                            p.backptr[((int64_t)slot_item[bb] * p.T + t) * S + j] = (uint16_t)min(arg, S - 1);
                     }
                 }
             }
@@ -257,8 +271,8 @@ WideGeometry wide_geometry(int64_t B, int64_t S, int sm_count) {
     const size_t ldp = (size_t)padded_sources(S);
     const size_t slice = sizeof(float) * g.R * ldp, budget = 200 * 1024;
     // as many sequences in lockstep as the batch has and shared memory holds
-    g.BC = B > 4 ? 16 : B > 1 ? 4 : 1;
-    while (g.BC > 1 && sizeof(float) * g.BC * ldp > budget) g.BC /= 4;
+    g.BC = B > 8 ? 16 : B > 4 ? 8 : B > 2 ? 4 : B > 1 ? 2 : 1;
+    while (g.BC > 1 && sizeof(float) * g.BC * ldp > budget) g.BC /= 2;
     const size_t scores = sizeof(float) * g.BC * ldp;
     (void)slice;
     g.resident_rows = scores < budget ? (int)std::min<size_t>(g.R, (budget - scores) / (sizeof(float) * ldp)) : 0;
@@ -277,12 +291,12 @@ bool forward_wide_supported(const ForwardArgs &a) {
 // Estimated seconds for the wide kernel: per step a fixed exchange + barrier cost
 // plus the max-plus work of the sequences still running (calibrated on the B200).
 double wide_estimate_seconds(const int32_t *frames_sorted, int64_t B, int64_t S, int sm_count) {
-    // B200 measurements (tools/calibrate_kernels.sh): S = 1440 fully resident: 3.1 / 6.6 / 20.0 us
-    // per step for 1 / 4 / 16 sequences; S = 4096 (11 of 28 rows resident): 8.2 / 30.6 us for 1 / 4.
+    // B200 measurements (tools/calibrate_kernels.sh): S = 1440 fully resident: 3.2 / 5.3 / 13.9 us
+    // per step for 1 / 4 / 16 sequences; S = 4096 (11 of 28 rows resident): 8.5 / 22 us for 1 / 4.
     const WideGeometry g = wide_geometry(B, S, sm_count);
     const double ldp = (double)padded_sources(S);
     const double rounds = (g.R + kWideWarps - 1) / kWideWarps;             // rows per warp
-    const double per_sequence_us = rounds * ldp * 0.00072;
+    const double per_sequence_us = rounds * ldp * 0.0005;
     const double streamed = 1.0 - (double)g.resident_rows / g.R;
     const double slice_stream_us = 4.0 * (double)padded_dests(S) * ldp * streamed / 5.0e6;   // ~5 TB/s of L2
     double total = 0.0;
@@ -335,9 +349,13 @@ cudaError_t launch_forward_wide(const ForwardArgs &a, cudaStream_t stream) {
     p.resident_rows = g.resident_rows;
     cudaError_t e = launch_pad_transition(a, stream);
     if (e != cudaSuccess) return e;
-    if (g.BC == 1) return launch_wide_t<1>(a, p, g.smem, stream);
-    if (g.BC == 4) return launch_wide_t<4>(a, p, g.smem, stream);
-    return launch_wide_t<16>(a, p, g.smem, stream);
+    switch (g.BC) {
+        case 1: return launch_wide_t<1>(a, p, g.smem, stream);
+        case 2: return launch_wide_t<2>(a, p, g.smem, stream);
+        case 4: return launch_wide_t<4>(a, p, g.smem, stream);
+        case 8: return launch_wide_t<8>(a, p, g.smem, stream);
+        default: return launch_wide_t<16>(a, p, g.smem, stream);
+    }
 }
 
 }  // namespace torbi_b200
