@@ -148,6 +148,13 @@ TORBI_B200_API void torbi_b200_release(void);
 TORBI_B200_API uint64_t torbi_b200_launch_count(void);
 TORBI_B200_API const char *torbi_b200_last_kernel(void);
 
+/* Which forward kernel a decode of this shape and length profile would use on a device with
+ * `sm_count` SMs ("forward_tiled", "forward_tiled_32", "forward_wide", "forward_generic", ...).
+ * Pure host logic -- no CUDA call -- so schedulers and tests can query the plan.  NULL on
+ * invalid arguments (see torbi_b200_last_error). */
+TORBI_B200_API const char *torbi_b200_plan(const int32_t *batch_frames, int64_t batch, int64_t frames,
+                                           int64_t states, uint32_t flags, int sm_count);
+
 /* Device time of the forward and the backtrace kernel of the last
  * torbi_b200_decode on this thread that was called with
  * TORBI_B200_TIME_KERNELS.  Waits for those kernels to finish.  Either pointer

@@ -51,6 +51,36 @@ def test_workspace_bytes_and_shape_validation():
     assert 'exceeds 65535' in _ffi.last_error()
 
 
+def plan(frames, T, S, flags=0, sm_count=148):
+    frames = np.ascontiguousarray(frames, dtype=np.int32)
+    name = _ffi.library().torbi_b200_plan(frames.ctypes.data, len(frames), T, S, flags, sm_count)
+    return name.decode() if name else None
+
+
+def test_kernel_plan_host_logic():
+    """Kernel selection is pure host logic (measured cost models): checked without a GPU."""
+    full = [2000] * 512
+    assert plan(full, 2000, 1440) == 'forward_tiled'                       # the headline shape: 64-row tiles
+    assert plan([2000] * 256, 2000, 1440) == 'forward_tiled_32'            # 8 groups need 8 batches
+    assert plan([2000] * 128, 2000, 1440) == 'forward_tiled_16'
+    assert plan([2000], 2000, 1440) == 'forward_wide'                      # config 1
+    assert plan([1000000], 1000000, 4096) == 'forward_wide'                # config 5
+    assert plan([2000] * 16, 2000, 1440) == 'forward_wide'
+    assert plan(full, 2000, 1440, _ffi.BANDED) == 'forward_tiled_banded'
+    assert plan(full, 2000, 1440, _ffi.TILED_WS) == 'forward_tiled_ws'
+    assert plan(full, 2000, 1440, _ffi.FORCE_GENERIC) == 'forward_generic'
+    assert plan(full, 2000, 1440, _ffi.TILE_ROWS_16) == 'forward_tiled_16'
+    # ragged, heavy tailed: smaller tiles shorten the critical path of the longest items
+    rng = np.random.default_rng(1234)
+    ragged = np.exp(rng.uniform(np.log(200), np.log(20000), size=256)).round().astype(np.int32)
+    assert plan(ragged, 20000, 1440) == 'forward_tiled_16'
+    # more destination tiles than SMs: no tiled kernel; 20000 states still fit the wide one
+    assert plan([4, 4], 4, 20000) == 'forward_wide'
+    assert plan([4, 4], 4, 20000, _ffi.FORCE_TILED) is None and 'tiled kernel' in _ffi.last_error()
+    assert plan([3], 3, 65535) == 'forward_generic'
+    assert plan([3], 3, 70000) is None
+
+
 def test_no_cpu_fallback():
     observation = torch.rand(1, 3, 3)
     with pytest.raises(RuntimeError, match='no CPU fallback'):

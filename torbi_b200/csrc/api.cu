@@ -138,6 +138,49 @@ size_t torbi_b200_workspace_bytes(int64_t B, int64_t T, int64_t S, uint32_t) {
 
 namespace {
 
+enum Choice { kGeneric, kTiled, kWide };
+
+// Kernel selection: estimated time of the batch-tiled and the wide decomposition for this
+// length profile (longest-first `order`), unless a flag forces one.  Also fixes a.tile_rows.
+int choose_kernel(ForwardArgs &a, const int32_t *batch_frames, const std::vector<int32_t> &order,
+                  uint32_t flags, Choice *out) {
+    const int64_t B = a.B, S = a.S;
+    std::vector<int32_t> sorted(B);
+    for (int64_t i = 0; i < B; ++i) sorted[i] = batch_frames[order[i]];
+    double tiled_seconds = 0.0;
+    a.tile_rows = tiled_choose_rows(sorted.data(), B, S, a.sm_count, &tiled_seconds);
+    if (flags & TORBI_B200_TILE_ROWS_MASK)
+        a.tile_rows = 16 << (((flags & TORBI_B200_TILE_ROWS_MASK) >> 12) - 1);
+    const bool can_tile = forward_tiled_supported(a), can_wide = forward_wide_supported(a);
+    Choice choice = kGeneric;
+    if (can_tile) choice = kTiled;
+    if (can_wide && (!can_tile || wide_estimate_seconds(sorted.data(), B, S, a.sm_count) < tiled_seconds))
+        choice = kWide;
+    if (flags & (TORBI_B200_FORCE_TILED | TORBI_B200_TILE_ROWS_MASK | TORBI_B200_BANDED)) {
+        if (!can_tile) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "tiled kernel does not support this shape");
+        choice = kTiled;
+    }
+    if (flags & TORBI_B200_FORCE_WIDE) {
+        if (!can_wide) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "wide kernel does not support this shape");
+        choice = kWide;
+    }
+    if (flags & TORBI_B200_FORCE_GENERIC) choice = kGeneric;
+    *out = choice;
+    return TORBI_B200_OK;
+}
+
+const char *kernel_name(const ForwardArgs &a, Choice choice, uint32_t flags) {
+    if (choice == kTiled && (flags & TORBI_B200_TILED_WS) && !(flags & TORBI_B200_BANDED) &&
+        forward_tiled_ws_supported(a))
+        return "forward_tiled_ws";
+    if (choice == kTiled) {
+        if (flags & TORBI_B200_BANDED)
+            return a.tile_rows == 64 ? "forward_tiled_banded" : a.tile_rows == 32 ? "forward_tiled_banded_32" : "forward_tiled_banded_16";
+        return a.tile_rows == 64 ? "forward_tiled" : a.tile_rows == 32 ? "forward_tiled_32" : "forward_tiled_16";
+    }
+    return choice == kWide ? "forward_wide" : "forward_generic";
+}
+
 // torbi_b200_decode plus `frames_ready`: a device word the forward kernel polls
 // when the observations are still being copied in (host entry); nullptr otherwise.
 // `*streamed` reports whether the chosen kernel honours it.
@@ -206,48 +249,22 @@ int decode_device(const float *observation, const int32_t *batch_frames,
         if (e != cudaSuccess) return fail_cuda(e, "timing events");
     }
 
-    // kernel selection: estimated time of the batch-tiled and the wide
-    // decomposition for this length profile, unless a flag forces one
-    std::vector<int32_t> sorted(B);
-    for (int64_t i = 0; i < B; ++i) sorted[i] = batch_frames[order[i]];
-    double tiled_seconds = 0.0;
-    a.tile_rows = tiled_choose_rows(sorted.data(), B, S, info.sm_count, &tiled_seconds);
-    if (flags & TORBI_B200_TILE_ROWS_MASK)
-        a.tile_rows = 16 << (((flags & TORBI_B200_TILE_ROWS_MASK) >> 12) - 1);
-    const bool can_tile = forward_tiled_supported(a), can_wide = forward_wide_supported(a);
-    enum { kGeneric, kTiled, kWide } choice = kGeneric;
-    if (can_tile) choice = kTiled;
-    if (can_wide && (!can_tile || wide_estimate_seconds(sorted.data(), B, S, info.sm_count) < tiled_seconds))
-        choice = kWide;
-    if (flags & (TORBI_B200_FORCE_TILED | TORBI_B200_TILE_ROWS_MASK | TORBI_B200_BANDED)) {
-        if (!can_tile) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "tiled kernel does not support this shape");
-        choice = kTiled;
-    }
-    if (flags & TORBI_B200_FORCE_WIDE) {
-        if (!can_wide) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "wide kernel does not support this shape");
-        choice = kWide;
-    }
-    if (flags & TORBI_B200_FORCE_GENERIC) choice = kGeneric;
+    Choice choice = kGeneric;
+    rc = choose_kernel(a, batch_frames, order, flags, &choice);
+    if (rc) return rc;
     const bool tiled = choice != kGeneric;               // kernels that honour frames_ready
     if (streamed) *streamed = tiled;
-    if (choice == kTiled && (flags & TORBI_B200_TILED_WS) && !(flags & TORBI_B200_BANDED) &&
-        forward_tiled_ws_supported(a)) {
-        e = launch_forward_tiled_ws(a, stream);
-        g_last_kernel = "forward_tiled_ws";
-    } else if (choice == kTiled) {
-        e = launch_forward_tiled(a, stream);
-        if (flags & TORBI_B200_BANDED)
-            g_last_kernel = a.tile_rows == 64 ? "forward_tiled_banded" : a.tile_rows == 32 ? "forward_tiled_banded_32" : "forward_tiled_banded_16";
-        else
-            g_last_kernel = a.tile_rows == 64 ? "forward_tiled" : a.tile_rows == 32 ? "forward_tiled_32" : "forward_tiled_16";
-    } else if (choice == kWide) {
-        e = launch_forward_wide(a, stream);
-        g_last_kernel = "forward_wide";
-    } else {
+    g_last_kernel = kernel_name(a, choice, flags);
+    if (choice == kGeneric) {
         if (frames_ready)
             return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "internal: generic kernel cannot stream");
         e = launch_forward_generic(a, stream);
-        g_last_kernel = "forward_generic";
+    } else if (choice == kWide) {
+        e = launch_forward_wide(a, stream);
+    } else if (!std::strcmp(g_last_kernel, "forward_tiled_ws")) {
+        e = launch_forward_tiled_ws(a, stream);
+    } else {
+        e = launch_forward_tiled(a, stream);
     }
     if (e != cudaSuccess) return fail_cuda(e, g_last_kernel);
     if (timed) cudaEventRecord(g_timing.ev[1], stream);
@@ -272,6 +289,25 @@ int torbi_b200_decode(const float *observation, const int32_t *batch_frames,
                       void *workspace, size_t workspace_bytes, void *stream) {
     return decode_device(observation, batch_frames, transition, initial, B, T, S, flags, indices,
                          posterior, workspace, workspace_bytes, stream, nullptr, nullptr);
+}
+
+const char *torbi_b200_plan(const int32_t *batch_frames, int64_t B, int64_t T, int64_t S,
+                            uint32_t flags, int sm_count) {
+    g_error[0] = 0;
+    if (validate_shape(B, T, S) != TORBI_B200_OK || !batch_frames || sm_count < 1) return nullptr;
+    std::vector<int32_t> order(pad_batch(B), -1);
+    std::iota(order.begin(), order.begin() + B, 0);
+    std::stable_sort(order.begin(), order.begin() + B,
+                     [&](int32_t x, int32_t y) { return batch_frames[x] > batch_frames[y]; });
+    ForwardArgs a{};
+    a.B = B; a.T = T; a.S = S;
+    a.flags = flags;
+    a.sm_count = sm_count;
+    a.ws = carve_workspace(reinterpret_cast<void *>(uintptr_t(256)), B, T, S);   // layout only, never dereferenced
+    a.observation = reinterpret_cast<const float *>(uintptr_t(256));
+    Choice choice = kGeneric;
+    if (choose_kernel(a, batch_frames, order, flags, &choice) != TORBI_B200_OK) return nullptr;
+    return kernel_name(a, choice, flags);
 }
 
 int torbi_b200_last_timing(float *forward_ms, float *backtrace_ms) {
