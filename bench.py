@@ -56,6 +56,8 @@ def parse_args():
     parser.add_argument('--kernel', default='auto', choices=['auto', 'generic', 'tiled', 'wide'])
     parser.add_argument('--tile-rows', type=int, default=0, choices=[0, 16, 32, 64])
     parser.add_argument('--ws', action='store_true', help='warp-specialised tiled kernel')
+    parser.add_argument('--backpointers', action='store_true',
+                        help="tiled kernel in backpointer mode (uint16 trellis) instead of score history + recomputed backtrace")
     parser.add_argument('--banded', action='store_true', help='exact banded-transition fast path (not the contract metric)')
     return parser.parse_args()
 
@@ -69,10 +71,11 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source='fallback (B200_PROFILING.md)')
 
 
-def profiled_traffic(kernel, args):
+def profiled_traffic(kernel, args, backtrace='backtrace_recompute'):
     """DRAM bytes (read + write) of one launch of the forward kernel from the
     committed `ncu --set full` capture of this same workload, or None."""
-    path = ROOT / 'profiles' / 'forward_tiled_ncu_full.json'
+    path = ROOT / 'profiles' / ('forward_tiled_hist_ncu_full.json' if backtrace == 'backtrace_recompute'
+                                else 'forward_tiled_ncu_full.json')
     if kernel != 'forward_tiled' or not path.exists() or \
             (args.batch, args.frames, args.states) != (512, 2000, 1440):
         return None
@@ -272,6 +275,8 @@ def bench_graft(args):
         flags |= _ffi.TILED_WS
     if args.banded:
         flags |= _ffi.BANDED
+    if args.backpointers:
+        flags |= _ffi.BACKPOINTERS
     timesteps_per_step = int(frames.sum())
 
     fwd_ms, back_ms = [], []
@@ -300,6 +305,7 @@ def bench_graft(args):
     elapsed_ms = start.elapsed_time(end)
     launches = lib.torbi_b200_launch_count() - launches0
     kernel = lib.torbi_b200_last_kernel().decode()
+    backtrace = lib.torbi_b200_last_backtrace().decode()
     checksum = int(indices.sum(dtype=torch.int64))
 
     # end to end through the C ABI host entry: pinned host buffers
@@ -342,7 +348,8 @@ def bench_graft(args):
         ops = 2.0 * S * S * timesteps_per_step
         achieved = ops / (kernel_ms * 1e-3) / 1e12
         peak = sm_count * 128 * peaks['sm_max_mhz'] * 1e6 / 1e12
-        hbm_bytes = (4.0 * S + 2.0 * S) * timesteps_per_step          # obs read + uint16 backpointers
+        # forward kernel: observation read + fp32 score history (or uint16 backpointers) written
+        hbm_bytes = (4.0 * S + (4.0 if backtrace == 'backtrace_recompute' else 2.0) * S) * timesteps_per_step
         hbm_achieved = hbm_bytes / (kernel_ms * 1e-3) / 1e9
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -357,10 +364,10 @@ def bench_graft(args):
             'clocks': clocks.summary(),
             'roofline': {
                 'bound': 'fp32_alu_issue', 'kernel': kernel, 'achieved': achieved, 'peak': peak,
-                'unit': 'T lane-op/s', 'frac': achieved / peak, 'traffic': profiled_traffic(kernel, args),
+                'unit': 'T lane-op/s', 'frac': achieved / peak, 'traffic': profiled_traffic(kernel, args, backtrace),
                 'traffic_note': 'DRAM read+write bytes per launch, ncu --set full capture in profiles/ (not live)',
                 'kernel_ms': kernel_ms, 'kernel_share_of_step': kernel_ms * args.steps / elapsed_ms,
-                'backtrace_ms': statistics.mean(back_ms),
+                'backtrace_ms': statistics.mean(back_ms), 'backtrace': backtrace,
                 'ops_per_launch': ops, 'peak_source': f"{sm_count} SMs x 128 lanes x {peaks['sm_max_mhz']} MHz, {peaks['source']}",
                 'timesteps_per_s_at_peak': peak * 1e12 / (2.0 * S * S),
                 'hbm': {'bound': 'hbm', 'achieved': hbm_achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',

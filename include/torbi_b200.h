@@ -69,6 +69,15 @@ extern "C" {
  * constant; the dense loop runs over the window only and the rest is a first-occurrence max
  * of P[s] + constant.  Bit-identical results for ANY matrix, faster when it is banded. */
 #define TORBI_B200_BANDED (1u << 15)
+/* The tiled kernel has two ways of producing the path.  Default (score-history mode): the forward
+ * pass is a pure max-plus product that keeps every fp32 score vector P_t (4 bytes per (b,t,s) in
+ * the workspace) and the backtrace recomputes, per step, the one argmax that lies on the decoded
+ * path -- idx_{t-1} = lowest s maximising P_{t-1}[s] + A[idx_t][s], the forward pass's own fp32 add,
+ * hence the same result bit for bit.  With this flag the kernel tracks the argmax of every state
+ * and stores uint16 backpointers (2 bytes per (b,t,s)) like the reference's trellis
+ * (viterbi.cpp:91-104); slower, half the workspace.  Pass the same flag to
+ * torbi_b200_workspace_bytes.  The wide and generic kernels always store backpointers. */
+#define TORBI_B200_BACKPOINTERS (1u << 16)
 /* use the warp-specialised variant of the tiled kernel (64-row batches, S % 8 == 0) */
 #define TORBI_B200_TILED_WS (1u << 14)
 
@@ -81,7 +90,8 @@ TORBI_B200_API const char *torbi_b200_last_error(void);
 TORBI_B200_API int torbi_b200_device_count(void);
 
 /* Bytes of device workspace torbi_b200_decode needs for this shape
- * (uint16 backpointers B*T*S*2, ping-pong forward scores, scheduling state).
+ * (fp32 score history B*T*S*4 -- or uint16 backpointers B*T*S*2 with
+ * TORBI_B200_BACKPOINTERS --, rotating forward scores, scheduling state).
  * Returns 0 on invalid shape. */
 TORBI_B200_API size_t torbi_b200_workspace_bytes(int64_t batch, int64_t frames, int64_t states, uint32_t flags);
 
@@ -147,6 +157,8 @@ TORBI_B200_API void torbi_b200_release(void);
  * name of the forward kernel the last decode on this thread used. */
 TORBI_B200_API uint64_t torbi_b200_launch_count(void);
 TORBI_B200_API const char *torbi_b200_last_kernel(void);
+/* "backtrace" (stored uint16 backpointers) or "backtrace_recompute" (score-history mode) */
+TORBI_B200_API const char *torbi_b200_last_backtrace(void);
 
 /* Which forward kernel a decode of this shape and length profile would use on a device with
  * `sm_count` SMs ("forward_tiled", "forward_tiled_32", "forward_wide", "forward_generic", ...).

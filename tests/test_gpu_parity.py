@@ -14,7 +14,10 @@ pytestmark = pytest.mark.gpu
 KERNELS = {'auto': 0, 'generic': _ffi.FORCE_GENERIC, 'tiled16': _ffi.TILE_ROWS_16,
            'tiled32': _ffi.TILE_ROWS_32, 'tiled64': _ffi.TILE_ROWS_64, 'wide': _ffi.FORCE_WIDE,
            'tiled64ws': _ffi.TILE_ROWS_64 | _ffi.TILED_WS, 'banded': _ffi.BANDED,
-           'banded16': _ffi.BANDED | _ffi.TILE_ROWS_16}
+           'banded16': _ffi.BANDED | _ffi.TILE_ROWS_16,
+           # the tiled kernel's backpointer mode (default is score history + recomputed backtrace)
+           'tiled64bp': _ffi.TILE_ROWS_64 | _ffi.BACKPOINTERS, 'tiled16bp': _ffi.TILE_ROWS_16 | _ffi.BACKPOINTERS,
+           'tiled32bp': _ffi.TILE_ROWS_32 | _ffi.BACKPOINTERS, 'bandedbp': _ffi.BANDED | _ffi.BACKPOINTERS}
 
 
 def bits(a):
@@ -456,3 +459,21 @@ def test_file_drivers(tmp_path, oracle):
             assert np.array_equal(torch.load(out).numpy(), want)
     finally:
         torbi_b200.MIN_CHUNK_SIZE = None
+
+
+def test_tiled_kernel_modes_report_their_backtrace(oracle):
+    """Score-history mode (default) and backpointer mode of the tiled kernel agree bit for bit and
+    report which backtrace ran; the workspace is sized per mode."""
+    lib = _ffi.library()
+    obs, frames, A, init = random_problem(77, 70, 40, 1440, quant=1)      # quantised: many exact ties
+    want_idx, want_post = oracle.c_decode(obs, frames, A, init, exact_scan=False, want_posterior=True)
+    for flags, name in ((_ffi.FORCE_TILED, 'backtrace_recompute'),
+                        (_ffi.FORCE_TILED | _ffi.BACKPOINTERS, 'backtrace'),
+                        (_ffi.FORCE_WIDE, 'backtrace'), (_ffi.FORCE_GENERIC, 'backtrace')):
+        indices, posterior = gpu_decode(obs, frames, A, init, flags=flags)
+        assert lib.torbi_b200_last_backtrace().decode() == name
+        assert np.array_equal(indices, want_idx)
+        assert np.array_equal(bits(posterior), bits(want_post))
+    hist = lib.torbi_b200_workspace_bytes(70, 40, 1440, 0)
+    bp = lib.torbi_b200_workspace_bytes(70, 40, 1440, _ffi.BACKPOINTERS)
+    assert hist - bp == 2 * 70 * 40 * 1440

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_flag_values_match_header():
     header = (ROOT / 'include' / 'torbi_b200.h').read_text()
     for name in ('OBS_IS_PROBABILITY', 'EPS_FLOOR', 'FORCE_GENERIC', 'FORCE_TILED', 'FORCE_WIDE', 'TIME_KERNELS',
-                 'TILED_WS', 'BANDED'):
+                 'TILED_WS', 'BANDED', 'BACKPOINTERS'):
         shift = int(re.search(rf'#define TORBI_B200_{name} \(1u << (\d+)\)', header).group(1))
         assert getattr(_ffi, name) == 1 << shift
     for name, value in (('TILE_ROWS_16', 1), ('TILE_ROWS_32', 2), ('TILE_ROWS_64', 3)):
@@ -43,9 +43,11 @@ def test_flag_values_match_header():
 
 def test_workspace_bytes_and_shape_validation():
     lib = _ffi.library()
-    # uint16 backpointers dominate: B*T*S*2
-    assert lib.torbi_b200_workspace_bytes(512, 2000, 1440, 0) >= 512 * 2000 * 1440 * 2
-    assert lib.torbi_b200_workspace_bytes(512, 2000, 1440, 0) < 512 * 2000 * 1440 * 2 * 1.02
+    # the fp32 score history dominates (B*T*S*4), or uint16 backpointers (B*T*S*2) in backpointer mode
+    assert lib.torbi_b200_workspace_bytes(512, 2000, 1440, 0) >= 512 * 2000 * 1440 * 4
+    assert lib.torbi_b200_workspace_bytes(512, 2000, 1440, 0) < 512 * 2000 * 1440 * 4 * 1.01
+    assert lib.torbi_b200_workspace_bytes(512, 2000, 1440, _ffi.BACKPOINTERS) >= 512 * 2000 * 1440 * 2
+    assert lib.torbi_b200_workspace_bytes(512, 2000, 1440, _ffi.BACKPOINTERS) < 512 * 2000 * 1440 * 2 * 1.02
     assert lib.torbi_b200_workspace_bytes(0, 10, 10, 0) == 0
     assert lib.torbi_b200_workspace_bytes(1, 10, 65536, 0) == 0
     assert 'exceeds 65535' in _ffi.last_error()

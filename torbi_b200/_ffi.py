@@ -27,6 +27,7 @@ TILE_ROWS_32 = 2 << 12
 TILE_ROWS_64 = 3 << 12
 TILED_WS = 1 << 14
 BANDED = 1 << 15
+BACKPOINTERS = 1 << 16
 
 ABI_VERSION = 1
 
@@ -47,6 +48,7 @@ SIGNATURES = {
     'torbi_b200_release': (None, []),
     'torbi_b200_launch_count': (ctypes.c_uint64, []),
     'torbi_b200_last_kernel': (ctypes.c_char_p, []),
+    'torbi_b200_last_backtrace': (ctypes.c_char_p, []),
     'torbi_b200_last_timing': (ctypes.c_int, [_p, _p]),
     'torbi_b200_plan': (ctypes.c_char_p, [_p, _i64, _i64, _i64, ctypes.c_uint32, ctypes.c_int]),
 }

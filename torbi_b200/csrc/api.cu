@@ -24,6 +24,7 @@ namespace {
 
 thread_local char g_error[512] = "";
 thread_local const char *g_last_kernel = "none";
+thread_local const char *g_last_backtrace = "none";
 std::atomic<uint64_t> g_launches{0};
 
 // events for TORBI_B200_TIME_KERNELS, per host thread, bound to one device
@@ -114,6 +115,8 @@ uint64_t torbi_b200_launch_count(void) { return g_launches.load(); }
 
 const char *torbi_b200_last_kernel(void) { return g_last_kernel; }
 
+const char *torbi_b200_last_backtrace(void) { return g_last_backtrace; }
+
 int torbi_b200_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -129,9 +132,9 @@ int torbi_b200_device_count(void) {
     return usable;
 }
 
-size_t torbi_b200_workspace_bytes(int64_t B, int64_t T, int64_t S, uint32_t) {
+size_t torbi_b200_workspace_bytes(int64_t B, int64_t T, int64_t S, uint32_t flags) {
     if (validate_shape(B, T, S) != TORBI_B200_OK) return 0;
-    return carve_workspace(nullptr, B, T, S).bytes;
+    return carve_workspace(nullptr, B, T, S, flags).bytes;
 }
 
 }  // extern "C"
@@ -204,7 +207,7 @@ int decode_device(const float *observation, const int32_t *batch_frames,
     }
     if (reinterpret_cast<uintptr_t>(workspace) % 256)
         return fail(TORBI_B200_ERR_WORKSPACE, "workspace must be 256-byte aligned");
-    Workspace ws = carve_workspace(workspace, B, T, S);
+    Workspace ws = carve_workspace(workspace, B, T, S, flags);
     if (workspace_bytes < ws.bytes)
         return fail(TORBI_B200_ERR_WORKSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, ws.bytes);
 
@@ -255,6 +258,7 @@ int decode_device(const float *observation, const int32_t *batch_frames,
     const bool tiled = choice != kGeneric;               // kernels that honour frames_ready
     if (streamed) *streamed = tiled;
     g_last_kernel = kernel_name(a, choice, flags);
+    bool history = false;
     if (choice == kGeneric) {
         if (frames_ready)
             return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "internal: generic kernel cannot stream");
@@ -263,13 +267,19 @@ int decode_device(const float *observation, const int32_t *batch_frames,
         e = launch_forward_wide(a, stream);
     } else if (!std::strcmp(g_last_kernel, "forward_tiled_ws")) {
         e = launch_forward_tiled_ws(a, stream);
+    } else if (workspace_has_history(flags)) {
+        // score-history mode (default): pure max-plus forward, argmax recomputed along the path
+        history = true;
+        e = launch_forward_tiled_hist(a, stream);
     } else {
         e = launch_forward_tiled(a, stream);
     }
     if (e != cudaSuccess) return fail_cuda(e, g_last_kernel);
     if (timed) cudaEventRecord(g_timing.ev[1], stream);
-    e = launch_backtrace(ws, indices, B, T, S, stream);
-    if (e != cudaSuccess) return fail_cuda(e, "backtrace");
+    g_last_backtrace = history ? "backtrace_recompute" : "backtrace";
+    e = history ? launch_backtrace_recompute(ws, indices, B, T, S, stream)
+                : launch_backtrace(ws, indices, B, T, S, stream);
+    if (e != cudaSuccess) return fail_cuda(e, g_last_backtrace);
     if (timed) {
         cudaEventRecord(g_timing.ev[2], stream);
         g_timing.valid = true;
@@ -303,7 +313,7 @@ const char *torbi_b200_plan(const int32_t *batch_frames, int64_t B, int64_t T, i
     a.B = B; a.T = T; a.S = S;
     a.flags = flags;
     a.sm_count = sm_count;
-    a.ws = carve_workspace(reinterpret_cast<void *>(uintptr_t(256)), B, T, S);   // layout only, never dereferenced
+    a.ws = carve_workspace(reinterpret_cast<void *>(uintptr_t(256)), B, T, S, flags);   // layout only, never dereferenced
     a.observation = reinterpret_cast<const float *>(uintptr_t(256));
     Choice choice = kGeneric;
     if (choose_kernel(a, batch_frames, order, flags, &choice) != TORBI_B200_OK) return nullptr;
@@ -381,7 +391,7 @@ int decode_items_on_device(const float *observation, const int32_t *batch_frames
     const size_t init_bytes = align_up(sizeof(float) * S, 256);
     const size_t idx_bytes = align_up(sizeof(int32_t) * count * T, 256);
     const size_t post_bytes = posterior ? align_up(sizeof(float) * count * S, 256) : 0;
-    const size_t ws_bytes = carve_workspace(nullptr, count, T, S).bytes;
+    const size_t ws_bytes = carve_workspace(nullptr, count, T, S, flags).bytes;
     const size_t total = obs_bytes + tr_bytes + init_bytes + idx_bytes + post_bytes + ws_bytes + 256;
 
     cudaError_t e;

@@ -33,6 +33,144 @@ backtrace_kernel(const uint16_t *__restrict__ backptr, const int32_t *__restrict
     }
 }
 
+// ---------------------------------------------------------------------------
+// Backtrace by recomputation (score-history mode of the tiled forward kernel).
+// The forward pass kept every P_t (fp32) instead of S backpointers per step; only the
+// one backpointer per step that lies on the decoded path is ever needed:
+//   idx_{t-1} = lowest s maximising P_{t-1}[s] + A[idx_t][s]
+// -- the same single fp32 add and the same first-occurrence rule as the forward scan
+// (viterbi.cpp:94-101), so the result is bit-identical to chasing stored backpointers.
+// One warp per sequence; per step one row of A (L2-resident) and one row of the history
+// (prefetched into L2 kAhead steps early, then into registers one step early).
+// ---------------------------------------------------------------------------
+namespace {
+
+constexpr int kRecomputeThreads = 128;
+constexpr int kAhead = 8;
+
+// monotonic fp32 -> uint32 map (no NaNs), so the warp max is one REDUX instruction
+__device__ __forceinline__ unsigned ordered_bits(float v) {
+    const unsigned b = __float_as_uint(v);
+    return b ^ ((unsigned)((int)b >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
+}
+__device__ __forceinline__ float warp_max(float m) {
+    return from_ordered_bits(__reduce_max_sync(kFullMask, ordered_bits(m)));
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void prefetch_row(const float *row, int S, int lane) {
+    const char *base = reinterpret_cast<const char *>(row);
+    for (int off = lane * 128; off < S * 4; off += kWarp * 128) prefetch_l2(base + off);
+}
+
+// NK > 0: S % 4 == 0 and S <= 128 * NK -- a lane keeps its NK float4 groups of the row in registers.
+// NK == 0: any S, two passes over the row (max, then first index attaining it).
+template <int NK>
+__global__ void __launch_bounds__(kRecomputeThreads)
+backtrace_recompute_kernel(const float *__restrict__ history, const float *__restrict__ transition,
+                           int64_t lda, const int32_t *__restrict__ frames_d,
+                           const int32_t *__restrict__ final_state, int32_t *__restrict__ indices,
+                           int64_t B, int64_t T, int S) {
+    const int lane = threadIdx.x % kWarp;
+    const int64_t b = (int64_t)blockIdx.x * (kRecomputeThreads / kWarp) + threadIdx.x / kWarp;
+    if (b >= B) return;
+    const int frames = frames_d[b];
+    const int last = final_state[b];
+    int32_t *out = indices + b * T;
+    for (int64_t t = frames - 1 + lane; t < T; t += kWarp) out[t] = last;      // viterbi.cpp:219-221
+    const float *hist = history + b * T * S;
+    int idx = last;
+
+    if constexpr (NK > 0) {
+        bool valid[NK];
+#pragma unroll
+        for (int k = 0; k < NK; ++k) valid[k] = 4 * (lane + kWarp * k) < S;
+        float4 next[NK];                                  // history row for the coming step
+        auto load_row = [&](int64_t t) {
+            const float4 *row = reinterpret_cast<const float4 *>(hist + t * S) + lane;
+#pragma unroll
+            for (int k = 0; k < NK; ++k)
+                if (valid[k]) next[k] = __ldcs(row + kWarp * k);
+        };
+        for (int t = frames - 2; t >= 0 && t > frames - 2 - kAhead; --t) prefetch_row(hist + (int64_t)t * S, S, lane);
+        if (frames >= 2) load_row(frames - 2);
+        for (int t = frames - 1; t >= 1; --t) {
+            const float4 *arow = reinterpret_cast<const float4 *>(transition + (int64_t)idx * lda) + lane;
+            float4 v[NK];
+#pragma unroll
+            for (int k = 0; k < NK; ++k)
+                if (valid[k]) v[k] = __ldg(arow + kWarp * k);         // the dependent load of the step
+            float4 pc[NK];
+#pragma unroll
+            for (int k = 0; k < NK; ++k) pc[k] = next[k];
+            if (t >= 2) load_row(t - 2);                              // independent: overlaps
+            if (t - 2 - kAhead >= 0) prefetch_row(hist + (int64_t)(t - 2 - kAhead) * S, S, lane);
+            float m = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < NK; ++k) {
+                if (valid[k]) {
+                    v[k].x += pc[k].x; v[k].y += pc[k].y; v[k].z += pc[k].z; v[k].w += pc[k].w;
+                    m = fmaxf(fmaxf(fmaxf(m, v[k].x), fmaxf(v[k].y, v[k].z)), v[k].w);
+                }
+            }
+            m = warp_max(m);
+            unsigned first = 0x7fffffffu;
+#pragma unroll
+            for (int k = NK - 1; k >= 0; --k) {
+                if (valid[k]) {
+                    const unsigned s0 = 4 * (lane + kWarp * k);
+                    if (v[k].w == m) first = s0 + 3;
+                    if (v[k].z == m) first = s0 + 2;
+                    if (v[k].y == m) first = s0 + 1;
+                    if (v[k].x == m) first = s0;
+                }
+            }
+            first = __reduce_min_sync(kFullMask, first);
+            idx = first < (unsigned)S ? (int)first : 0;               // (NaN input only: outside the contract)
+            if (lane == 0) out[t - 1] = idx;
+        }
+    } else {
+        for (int t = frames - 1; t >= 1; --t) {
+            const float *prow = hist + (int64_t)(t - 1) * S;
+            const float *arow = transition + (int64_t)idx * lda;
+            if (t - 1 - kAhead >= 0) prefetch_row(hist + (int64_t)(t - 1 - kAhead) * S, S, lane);
+            float m = -INFINITY;
+            for (int s = lane; s < S; s += kWarp) m = fmaxf(m, __ldg(prow + s) + __ldg(arow + s));
+            m = warp_max(m);
+            unsigned first = 0x7fffffffu;
+            for (int s = lane; s < S; s += kWarp)
+                if (first == 0x7fffffffu && __ldg(prow + s) + __ldg(arow + s) == m) first = s;
+            first = __reduce_min_sync(kFullMask, first);
+            idx = first < (unsigned)S ? (int)first : 0;
+            if (lane == 0) out[t - 1] = idx;
+        }
+    }
+}
+
+}  // namespace
+
+// `transition` is the padded copy the tiled kernel made: (padded_dests, lda) with 16-byte aligned rows.
+cudaError_t launch_backtrace_recompute(const Workspace &ws, int32_t *indices, int64_t B, int64_t T,
+                                       int64_t S, cudaStream_t stream) {
+    const float *history = reinterpret_cast<const float *>(ws.backptr);
+    const int64_t lda = padded_sources(S);
+    const unsigned grid = (unsigned)((B + kRecomputeThreads / kWarp - 1) / (kRecomputeThreads / kWarp));
+    if (S % 4 == 0 && S <= 128 * 4)
+        backtrace_recompute_kernel<4><<<grid, kRecomputeThreads, 0, stream>>>(
+            history, ws.transition_pad, lda, ws.frames, ws.final_state, indices, B, T, (int)S);
+    else if (S % 4 == 0 && S <= 128 * 12)
+        backtrace_recompute_kernel<12><<<grid, kRecomputeThreads, 0, stream>>>(
+            history, ws.transition_pad, lda, ws.frames, ws.final_state, indices, B, T, (int)S);
+    else
+        backtrace_recompute_kernel<0><<<grid, kRecomputeThreads, 0, stream>>>(
+            history, ws.transition_pad, lda, ws.frames, ws.final_state, indices, B, T, (int)S);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_backtrace(const Workspace &ws, int32_t *indices, int64_t B, int64_t T,
                              int64_t S, cudaStream_t stream) {
     backtrace_kernel<<<(unsigned)B, kBacktraceThreads, 0, stream>>>(

@@ -49,7 +49,8 @@ struct Workspace {
     uint32_t *sync;         // scheduling / barrier words (zeroed per call)
     float *score[4];        // rotating forward-score buffers, (pad_batch, padded_sources) each
     float *transition_pad;  // (padded_dests, padded_sources) copy, -inf outside (S,S)
-    uint16_t *backptr;      // (B, T, S) uint16 backpointers; row 0 unused
+    uint16_t *backptr;      // (B, T, S) uint16 backpointers, row 0 unused -- or, in score-history mode,
+                            // the same region as fp32 (B, T, S) forward scores (4 bytes per entry)
     size_t bytes;
 };
 
@@ -70,7 +71,10 @@ inline int64_t padded_sources(int64_t S) { return (S + kStageSources - 1) / kSta
 inline int64_t padded_dests(int64_t S) { return (S + kTileDests - 1) / kTileDests * kTileDests; }
 inline int64_t pad_batch(int64_t B) { return (B + 127) / 128 * 128; }
 
-inline Workspace carve_workspace(void *base, int64_t B, int64_t T, int64_t S) {
+// `history`: size the backpointer region for fp32 scores (unless TORBI_B200_BACKPOINTERS is set)
+inline bool workspace_has_history(uint32_t flags) { return !(flags & TORBI_B200_BACKPOINTERS); }
+
+inline Workspace carve_workspace(void *base, int64_t B, int64_t T, int64_t S, uint32_t flags) {
     Workspace w{};
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -88,7 +92,8 @@ inline Workspace carve_workspace(void *base, int64_t B, int64_t T, int64_t S) {
     w.score[2] = static_cast<float *>(take(sizeof(float) * Bp * Sp));
     w.score[3] = static_cast<float *>(take(sizeof(float) * Bp * Sp));
     w.transition_pad = static_cast<float *>(take(sizeof(float) * padded_dests(S) * Sp));
-    w.backptr = static_cast<uint16_t *>(take(sizeof(uint16_t) * B * T * S));
+    w.backptr = static_cast<uint16_t *>(
+        take((workspace_has_history(flags) ? sizeof(float) : sizeof(uint16_t)) * B * T * S));
     w.bytes = off;
     return w;
 }

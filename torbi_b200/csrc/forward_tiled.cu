@@ -21,6 +21,13 @@
 // records the FIRST chunk attaining the final maximum, then that chunk is
 // re-scanned for the lowest s with P[s] + A[j][s] == max.  This reproduces the
 // reference's ascending strict-`>` scan (viterbi.cpp:94-101) bit for bit.
+//
+// Two builds of this file: forward_tiled.cu (backpointer mode: two-level argmax, uint16
+// backpointers, as described above) and forward_tiled_hist.cu, which defines
+// TORBI_TILED_HIST and compiles the SCORE-HISTORY mode: the K loop is a pure max-plus
+// product (no chunk bookkeeping, no re-scan), every P_t is also stored to an fp32
+// (B,T,S) history, and backtrace.cu recomputes the one argmax per step that lies on the
+// decoded path (exact: the same single fp32 add P_{t-1}[s] + A[j][s]).
 #include <algorithm>
 #include <vector>
 
@@ -28,10 +35,15 @@
 #include "kernels.cuh"
 #include "sync.cuh"
 
+#ifndef TORBI_TILED_HIST
+#define TORBI_TILED_HIST 0
+#endif
+
 namespace torbi_b200 {
 
 namespace {
 
+constexpr bool kHist = TORBI_TILED_HIST;
 constexpr int TN = kTileDests;  // destination states per CTA (columns of the tile)
 constexpr int KC = 32;          // source states per argmax chunk
 constexpr int KS = kStageSources;  // source states per pipeline stage (3 chunks)
@@ -111,6 +123,7 @@ struct TiledParams {
     float *score0;              // 3 rotating buffers (Bpad, LDP), `score_stride` floats apart;
     int64_t score_stride;       // row = position in `order`
     uint16_t *backptr;          // (B,T,S)
+    float *history;             // score-history mode: (B,T,S) fp32, every P_t (same memory as backptr)
     float *posterior;           // (B,S) or null
     int32_t *final_state;       // (B,)
     unsigned *sync;             // per group: barrier counter (+0) and current batch (+1); queue head at [0] of the last line
@@ -237,6 +250,9 @@ __device__ __forceinline__ void rescan_tile(const float *best_tile, uint16_t *bp
     }
 }
 
+#if TORBI_TILED_HIST
+#define forward_tiled_kernel forward_tiled_hist_kernel      // distinct name in profiles
+#endif
 template <int M, uint32_t kFlags, bool kBanded>
 __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledParams p) {
     constexpr int TM = tile_rows(M);
@@ -309,6 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
     const int k_lo = s_lo * KS, k_hi = min(s_hi * KS, S);
     const bool obs_vec = (S % 4) == 0 && (reinterpret_cast<uintptr_t>(p.observation) & 15) == 0;
     const bool bp_vec = (S % 8) == 0;
+    const bool hist_vec = (S % 4) == 0;
     // loader mapping (see load_stage)
     const int ld_c4 = tid % (KS / 4), ld_r0 = tid / (KS / 4);
     const int ld_smem = ld_r0 * LDS_ + ld_c4 * 4;
@@ -347,7 +364,9 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                 const float *obs = p.observation + (int64_t)max(item, 0) * p.T * S;
                 for (int c = j0 + lane; c < c_end; c += kWarp) {
                     if (item >= 0 && c < S) {
-                        dst0[c] = convert_observation<kFlags>(obs[c]) + p.initial[c];
+                        const float v = convert_observation<kFlags>(obs[c]) + p.initial[c];
+                        dst0[c] = v;
+                        if (kHist) p.history[(int64_t)item * p.T * S + c] = v;
                     } else {
                         dst0[c] = 0.f;                   // padding stays finite, in all buffers
                         dst1[c] = 0.f;
@@ -523,7 +542,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                     for (int i = 0; i < M; ++i)
 #pragma unroll
                         for (int c = 0; c < N; ++c) {
-                            if (acc[i][c] > cur[i][c]) bestc[i][c] = chunk;   // first chunk reaching the max
+                            if (!kHist && acc[i][c] > cur[i][c]) bestc[i][c] = chunk;   // first chunk reaching the max
                             cur[i][c] = acc[i][c];
                         }
                 }
@@ -549,8 +568,10 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                         if (j0 + col < S) {
                             const float emit = convert_observation<kFlags>(tile[r * TN + col]);
                             tile[r * TN + col] = emit + (kBanded ? fmaxf(cur[i][c], out_v[r]) : cur[i][c]);
-                            best_tile[r * TN + col] = cur[i][c];
-                            bp_tile[r * TN + col] = (uint16_t)bestc[i][c];
+                            if (!kHist) {
+                                best_tile[r * TN + col] = cur[i][c];
+                                bp_tile[r * TN + col] = (uint16_t)bestc[i][c];
+                            }
                         }
                     }
                 }
@@ -564,13 +585,22 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                 if (col >= S || slot_item[r] < 0) continue;       // padding never changes
                 const int64_t off = (row0 + r) * LDP + col;
                 const bool live = t < slot_frames[r];
+                // score-history mode: P_t of live rows also goes to the (B,T,S) history (streaming store)
+                float *hist = (kHist && live) ? p.history + ((int64_t)slot_item[r] * p.T + t) * S + col : nullptr;
                 if (col + 3 < S) {
                     const float4 v = live ? *reinterpret_cast<const float4 *>(tile + r * TN + c4 * 4)
                                           : __ldcg(reinterpret_cast<const float4 *>(P_cur + off));
                     *reinterpret_cast<float4 *>(P_new + off) = v;
+                    if (kHist && live) {
+                        if (hist_vec) __stcs(reinterpret_cast<float4 *>(hist), v);
+                        else { hist[0] = v.x; hist[1] = v.y; hist[2] = v.z; hist[3] = v.w; }
+                    }
                 } else {
-                    for (int e = 0; col + e < S; ++e)
-                        P_new[off + e] = live ? tile[r * TN + c4 * 4 + e] : __ldcg(P_cur + off + e);
+                    for (int e = 0; col + e < S; ++e) {
+                        const float v = live ? tile[r * TN + c4 * 4 + e] : __ldcg(P_cur + off + e);
+                        P_new[off + e] = v;
+                        if (kHist && live) hist[e] = v;
+                    }
                 }
             }
             barriers += p.NJT;
@@ -580,14 +610,13 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             // ---- exact argmax while the rest of the group catches up: lowest s in the
             //      winning chunk with P[s] + A[j][s] == max.  8 lanes share one output
             //      (a float4 of the chunk each), so every load is a coalesced 128-byte row.
-#ifndef TORBI_EXPERIMENT_SKIP_RESCAN      // timing experiments only: results are wrong without it
+            if constexpr (!kHist) {
             if (j0 + TN <= S)
                 rescan_tile<TM, true, kBanded>(best_tile, bp_tile, slot_frames, P_cur + row0 * LDP,
                                                p.transition + (int64_t)j0 * LDP, LDP, S - j0, S, t, out_v, out_i);
             else
                 rescan_tile<TM, false, kBanded>(best_tile, bp_tile, slot_frames, P_cur + row0 * LDP,
                                                 p.transition + (int64_t)j0 * LDP, LDP, S - j0, S, t, out_v, out_i);
-#endif
             __syncthreads();
 
             // ---- backpointers: coalesced, vectorised uint16 stores ----
@@ -605,6 +634,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                         p.backptr[((int64_t)slot_item[r] * p.T + t) * S + j0 + c] = bp_tile[idx];
                 }
             }
+            }   // !kHist
             group_wait(counter, barriers);
         }
 
@@ -675,19 +705,21 @@ __global__ void analyze_band_kernel(const float *__restrict__ transition, int S,
 
 }  // namespace
 
+static int64_t tiled_ldp(int64_t S) { return padded_sources(S); }
+static int64_t tiled_sj(int64_t S) { return padded_dests(S); }
+
+#if !TORBI_TILED_HIST
 cudaError_t launch_pad_transition(const ForwardArgs &a, cudaStream_t stream) {
     pad_transition_kernel<<<a.sm_count * 4, 256, 0, stream>>>(
         a.transition, a.ws.transition_pad, (int)a.S, (int)padded_dests(a.S), (int)padded_sources(a.S));
     return cudaGetLastError();
 }
 
-static int64_t tiled_ldp(int64_t S) { return padded_sources(S); }
-static int64_t tiled_sj(int64_t S) { return padded_dests(S); }
-
 bool forward_tiled_supported(const ForwardArgs &a) {
     const int64_t njt = tiled_sj(a.S) / TN;
     return njt <= a.sm_count && a.ws.transition_pad != nullptr;
 }
+#endif
 
 template <int M, uint32_t kFlags, bool kBanded>
 static cudaError_t launch_tiled_t(const ForwardArgs &a, cudaStream_t stream) {
@@ -701,6 +733,7 @@ static cudaError_t launch_tiled_t(const ForwardArgs &a, cudaStream_t stream) {
     p.score0 = a.ws.score[0];
     p.score_stride = a.ws.score[1] - a.ws.score[0];
     p.backptr = a.ws.backptr;
+    p.history = reinterpret_cast<float *>(a.ws.backptr);
     p.posterior = a.posterior;
     p.final_state = a.ws.final_state;
     p.sync = a.ws.sync;
@@ -749,6 +782,7 @@ static cudaError_t launch_tiled_m(const ForwardArgs &a, cudaStream_t stream) {
     }
 }
 
+#if !TORBI_TILED_HIST
 // Relative cost of one timestep of a TM-row batch (measured on the B200, S = 1440).
 static double step_cost(int tm) { return tm == 64 ? 1.0 : tm == 32 ? 0.57 : 0.46; }
 
@@ -777,7 +811,13 @@ int tiled_choose_rows(const int32_t *frames_sorted, int64_t B, int64_t S, int sm
     return best_tm;
 }
 
+#endif
+
+#if TORBI_TILED_HIST
+cudaError_t launch_forward_tiled_hist(const ForwardArgs &a, cudaStream_t stream) {
+#else
 cudaError_t launch_forward_tiled(const ForwardArgs &a, cudaStream_t stream) {
+#endif
     switch (a.tile_rows) {
         case 16: return launch_tiled_m<1>(a, stream);
         case 32: return launch_tiled_m<2>(a, stream);

@@ -27,6 +27,9 @@ cudaError_t launch_forward_generic(const ForwardArgs &a, cudaStream_t stream);
 // forward_tiled.cu -- batch-tiled max-plus "GEMM" per timestep, persistent grid
 bool forward_tiled_supported(const ForwardArgs &a);
 cudaError_t launch_forward_tiled(const ForwardArgs &a, cudaStream_t stream);
+// forward_tiled_hist.cu -- the same kernel in score-history mode (no argmax bookkeeping; the
+// workspace's backpointer region holds fp32 (B,T,S) forward scores for launch_backtrace_recompute)
+cudaError_t launch_forward_tiled_hist(const ForwardArgs &a, cudaStream_t stream);
 int tiled_choose_rows(const int32_t *frames_sorted, int64_t B, int64_t S, int sm_count,
                       double *seconds);
 cudaError_t launch_pad_transition(const ForwardArgs &a, cudaStream_t stream);
@@ -43,5 +46,9 @@ cudaError_t launch_forward_wide(const ForwardArgs &a, cudaStream_t stream);
 // backtrace.cu -- ragged backtrace + tail fill (viterbi.cpp:140-160, :219-221)
 cudaError_t launch_backtrace(const Workspace &ws, int32_t *indices, int64_t B, int64_t T,
                              int64_t S, cudaStream_t stream);
+
+// backtrace by recomputation from the fp32 score history (tiled kernel, score-history mode)
+cudaError_t launch_backtrace_recompute(const Workspace &ws, int32_t *indices, int64_t B, int64_t T,
+                                       int64_t S, cudaStream_t stream);
 
 }  // namespace torbi_b200
