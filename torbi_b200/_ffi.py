@@ -6,9 +6,12 @@ in-tree by `make -C torbi_b200/csrc` (or __graft_entry__.build()); if it is
 missing every decode fails loudly -- there is no Python or CPU fallback.
 """
 import ctypes
+import os
 import pathlib
 
-LIBRARY = pathlib.Path(__file__).resolve().parent / 'libtorbi_b200.so'
+# TORBI_B200_LIBRARY: load another build of the same ABI (instrumented builds of tools/)
+LIBRARY = pathlib.Path(os.environ.get('TORBI_B200_LIBRARY') or
+                       pathlib.Path(__file__).resolve().parent / 'libtorbi_b200.so')
 
 OK = 0
 ERR_INVALID_ARGUMENT = -1

@@ -44,6 +44,22 @@ namespace torbi_b200 {
 namespace {
 
 constexpr bool kHist = TORBI_TILED_HIST;
+
+// Per-phase cycle counters of the step loop (thread 0 of a few CTAs prints them at the end);
+// compiled in only by tools/profile_phases.sh, never in the shipped library.
+#ifdef TORBI_TILED_PROFILE
+#define PROF_DECL long long prof_t0 = clock64(), prof_acc[5] = {0, 0, 0, 0, 0};
+#define PROF_MARK(i) { const long long prof_now = clock64(); prof_acc[i] += prof_now - prof_t0; prof_t0 = prof_now; }
+#define PROF_PRINT(steps)                                                                          \
+    if (threadIdx.x == 0 && blockIdx.x % 37 == 0)                                                  \
+        printf("cta %d steps %d cycles/step: first-stage wait %lld, K loop %lld, epilogue+publish+arrive %lld, " \
+               "prefetch(+rescan, backpointers) %lld, exchange wait %lld\n", blockIdx.x, (steps),        \
+               prof_acc[0] / (steps), prof_acc[1] / (steps), prof_acc[2] / (steps), prof_acc[3] / (steps), prof_acc[4] / (steps));
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#define PROF_PRINT(steps)
+#endif
 constexpr int TN = kTileDests;  // destination states per CTA (columns of the tile)
 constexpr int KC = 32;          // source states per argmax chunk
 constexpr int KS = kStageSources;  // source states per pipeline stage (3 chunks)
@@ -409,6 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
         if (batch_frames > 1) prefetch_step(1);
 
         int buf = 0;                                    // buffer holding P_{t-1}
+        PROF_DECL
         for (int t = 1; t < batch_frames; ++t) {
             // three rotating buffers: a CTA that is already publishing step t+1 never
             // writes the buffer a slower CTA of the group still re-scans for step t
@@ -499,6 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                 const unsigned slot = stage_counter % NSTAGE;
                 // every thread's copies for this stage have landed
                 mbar_wait(full_bar + slot, (stage_counter / NSTAGE) & 1);
+                if (s == 0) { PROF_MARK(0) }
                 const bool refill = s + 2 < nstages;
                 const unsigned rslot = (stage_counter + 2) % NSTAGE;          // the previous stage's slot
                 float *refill_dst = ring + rslot * kStageFloats + ld_smem;
@@ -556,6 +574,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                 cp_async_wait<0>();
                 __syncthreads();
             }
+            PROF_MARK(1)
 
             // ---- new scores: obs[t][j] + max  (viterbi.cpp:102); keep max and winning chunk ----
 #pragma unroll
@@ -605,6 +624,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             }
             barriers += p.NJT;
             group_arrive(counter);
+            PROF_MARK(2)
             if (t + 1 < batch_frames) prefetch_step(t + 1);   // `tile` is free: the publish above was its last reader
 
             // ---- exact argmax while the rest of the group catches up: lowest s in the
@@ -635,8 +655,11 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                 }
             }
             }   // !kHist
+            PROF_MARK(3)
             group_wait(counter, barriers);
+            PROF_MARK(4)
         }
+        PROF_PRINT(max(batch_frames - 1, 1))
 
         // ---- final scores out (viterbi.cpp:111-113) + first-occurrence argmax (:218) ----
         const float *P_fin = p.score0 + buf * p.score_stride;
