@@ -173,6 +173,12 @@ TORBI_B200_API const char *torbi_b200_plan(const int32_t *batch_frames, int64_t 
  * may be NULL. */
 TORBI_B200_API int torbi_b200_last_timing(float *forward_ms, float *backtrace_ms);
 
+/* Self-test: the kernels skip logf(expf(x) + FLT_MIN) where it is the identity (every fp32 x in
+ * (-64, -4], found exhaustively).  Evaluates the shortcut and the plain formula for ALL 2^32 fp32
+ * bit patterns on the current device and reports how many disagree (must be 0).  Takes ~1 s;
+ * allocates 8 bytes of device memory for the duration of the call. */
+TORBI_B200_API int torbi_b200_selftest_conversion(uint64_t *mismatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -477,3 +477,12 @@ def test_tiled_kernel_modes_report_their_backtrace(oracle):
     hist = lib.torbi_b200_workspace_bytes(70, 40, 1440, 0)
     bp = lib.torbi_b200_workspace_bytes(70, 40, 1440, _ffi.BACKPOINTERS)
     assert hist - bp == 2 * 70 * 40 * 1440
+
+
+def test_eps_floor_shortcut_is_exact_for_every_fp32_input():
+    """The kernels return x unchanged where logf(expf(x) + FLT_MIN) == x; the library checks that
+    shortcut against the plain formula for all 2^32 bit patterns on this device."""
+    import ctypes
+    mismatches = ctypes.c_uint64(123)
+    _ffi.check(_ffi.library().torbi_b200_selftest_conversion(ctypes.byref(mismatches)))
+    assert mismatches.value == 0

@@ -53,6 +53,7 @@ SIGNATURES = {
     'torbi_b200_last_kernel': (ctypes.c_char_p, []),
     'torbi_b200_last_backtrace': (ctypes.c_char_p, []),
     'torbi_b200_last_timing': (ctypes.c_int, [_p, _p]),
+    'torbi_b200_selftest_conversion': (ctypes.c_int, [_p]),
     'torbi_b200_plan': (ctypes.c_char_p, [_p, _i64, _i64, _i64, ctypes.c_uint32, ctypes.c_int]),
 }
 

@@ -567,6 +567,26 @@ int torbi_b200_decode_host_multi(const float *observation, const int32_t *batch_
     return TORBI_B200_OK;
 }
 
+int torbi_b200_selftest_conversion(uint64_t *mismatches) {
+    g_error[0] = 0;
+    if (!mismatches) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
+    DeviceInfo info;
+    int rc = device_info(device, &info);
+    if (rc) return rc;
+    unsigned long long *d = nullptr, h = 0;
+    e = cudaMalloc(&d, sizeof(h));
+    if (e == cudaSuccess) e = cudaMemset(d, 0, sizeof(h));
+    if (e == cudaSuccess) e = launch_selftest_conversion(d, info.sm_count, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    if (d) cudaFree(d);
+    if (e != cudaSuccess) return fail_cuda(e, "conversion self-test");
+    *mismatches = h;
+    return TORBI_B200_OK;
+}
+
 void torbi_b200_release(void) {
     std::lock_guard<std::mutex> lock(g_arena_mutex);
     for (auto &kv : g_arenas) {

@@ -20,17 +20,31 @@ constexpr unsigned kFullMask = 0xffffffffu;
 //     torch.exp_(observation); observation += finfo(float32).tiny; torch.log_(observation)
 // with the CUDA math library's expf/logf (what torch's CUDA exp/log kernels
 // call), no fast-math, no flush-to-zero.
+//
+// eps_floor(): logf(expf(x) + FLT_MIN) is the identity, bit for bit, for every fp32 x in
+// (-64, -4] -- where log-probabilities of a few thousand states live -- so the two
+// transcendental calls are skipped there.  This is not an approximation: the range was found
+// by evaluating all 2^32 inputs on the device (tools/probe_conversion.cu,
+// profiles/r01_conversion_identity_probe.txt) and torbi_b200_selftest_conversion re-checks
+// eps_floor against the plain formula for all 2^32 inputs (tests/test_gpu_parity.py).
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ float eps_floor_reference(float x) { return logf(expf(x) + FLT_MIN); }
+
+__device__ __forceinline__ float eps_floor(float x) {
+    if (x <= -4.f && x > -64.f) return x;
+    return eps_floor_reference(x);
+}
+
 template <uint32_t kFlags>
 __device__ __forceinline__ float convert_observation(float x) {
     if constexpr (kFlags & TORBI_B200_OBS_IS_PROBABILITY) x = logf(x);
-    if constexpr (kFlags & TORBI_B200_EPS_FLOOR) x = logf(expf(x) + FLT_MIN);
+    if constexpr (kFlags & TORBI_B200_EPS_FLOOR) x = eps_floor(x);
     return x;
 }
 
 __device__ __forceinline__ float convert_observation_rt(float x, uint32_t flags) {
     if (flags & TORBI_B200_OBS_IS_PROBABILITY) x = logf(x);
-    if (flags & TORBI_B200_EPS_FLOOR) x = logf(expf(x) + FLT_MIN);
+    if (flags & TORBI_B200_EPS_FLOOR) x = eps_floor(x);
     return x;
 }
 

@@ -48,13 +48,15 @@ constexpr bool kHist = TORBI_TILED_HIST;
 // Per-phase cycle counters of the step loop (thread 0 of a few CTAs prints them at the end);
 // compiled in only by tools/profile_phases.sh, never in the shipped library.
 #ifdef TORBI_TILED_PROFILE
-#define PROF_DECL long long prof_t0 = clock64(), prof_acc[5] = {0, 0, 0, 0, 0};
+#define PROF_DECL long long prof_t0 = clock64(), prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define PROF_MARK(i) { const long long prof_now = clock64(); prof_acc[i] += prof_now - prof_t0; prof_t0 = prof_now; }
 #define PROF_PRINT(steps)                                                                          \
     if (threadIdx.x == 0 && blockIdx.x % 37 == 0)                                                  \
-        printf("cta %d steps %d cycles/step: first-stage wait %lld, K loop %lld, epilogue+publish+arrive %lld, " \
-               "prefetch(+rescan, backpointers) %lld, exchange wait %lld\n", blockIdx.x, (steps),        \
-               prof_acc[0] / (steps), prof_acc[1] / (steps), prof_acc[2] / (steps), prof_acc[3] / (steps), prof_acc[4] / (steps));
+        printf("cta %d steps %d cycles/step: first-stage wait %lld, K loop %lld, epilogue %lld (new scores %lld + "  \
+               "CTA barrier %lld + publish %lld + arrive %lld), prefetch(+rescan, backpointers) %lld, exchange wait %lld\n", \
+               blockIdx.x, (steps), prof_acc[0] / (steps), prof_acc[1] / (steps),                               \
+               (prof_acc[2] + prof_acc[5] + prof_acc[6] + prof_acc[7]) / (steps), prof_acc[5] / (steps),          \
+               prof_acc[6] / (steps), prof_acc[7] / (steps), prof_acc[2] / (steps), prof_acc[3] / (steps), prof_acc[4] / (steps));
 #else
 #define PROF_DECL
 #define PROF_MARK(i)
@@ -595,7 +597,9 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                     }
                 }
             }
+            PROF_MARK(5)
             __syncthreads();
+            PROF_MARK(6)
 
             // ---- publish the new scores (finished rows are carried over), then arrive ----
             for (int idx = tid; idx < TM * (TN / 4); idx += kThreads) {
@@ -623,6 +627,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                 }
             }
             barriers += p.NJT;
+            PROF_MARK(7)
             group_arrive(counter);
             PROF_MARK(2)
             if (t + 1 < batch_frames) prefetch_step(t + 1);   // `tile` is free: the publish above was its last reader

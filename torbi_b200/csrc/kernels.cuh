@@ -51,4 +51,7 @@ cudaError_t launch_backtrace(const Workspace &ws, int32_t *indices, int64_t B, i
 cudaError_t launch_backtrace_recompute(const Workspace &ws, int32_t *indices, int64_t B, int64_t T,
                                        int64_t S, cudaStream_t stream);
 
+// selftest.cu
+cudaError_t launch_selftest_conversion(unsigned long long *mismatches, int sm_count, cudaStream_t stream);
+
 }  // namespace torbi_b200
