@@ -62,6 +62,8 @@ struct Workspace {
     int32_t *final_state;   // (B,)  argmax of the final forward scores
     uint32_t *sync;         // scheduling / barrier words (zeroed per call)
     float *score[4];        // rotating forward-score buffers, (pad_batch, padded_sources) each
+    float *block_max;       // 3 x (pad_batch, padded_sources / 16): max of each 16-state block of the rotating
+                            // score rows (banded mode: the outside-window maximum comes from these)
     float *transition_pad;  // (padded_dests, padded_sources) copy, -inf outside (S,S)
     uint16_t *backptr;      // (B, T, S) uint16 backpointers, row 0 unused -- or, in score-history mode,
                             // the same region as fp32 (B, T, S) forward scores (4 bytes per entry)
@@ -105,6 +107,7 @@ inline Workspace carve_workspace(void *base, int64_t B, int64_t T, int64_t S, ui
     w.score[1] = static_cast<float *>(take(sizeof(float) * Bp * Sp));
     w.score[2] = static_cast<float *>(take(sizeof(float) * Bp * Sp));
     w.score[3] = static_cast<float *>(take(sizeof(float) * Bp * Sp));
+    w.block_max = static_cast<float *>(take(sizeof(float) * 3 * Bp * (Sp / 16)));
     w.transition_pad = static_cast<float *>(take(sizeof(float) * padded_dests(S) * Sp));
     w.backptr = static_cast<uint16_t *>(
         take((workspace_has_history(flags) ? sizeof(float) : sizeof(uint16_t)) * B * T * S));

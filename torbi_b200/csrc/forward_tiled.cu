@@ -146,6 +146,8 @@ struct TiledParams {
     int32_t *final_state;       // (B,)
     unsigned *sync;             // per group: barrier counter (+0) and current batch (+1); queue head at [0] of the last line
     const int32_t *frames_ready;  // frames of `observation` copied in so far, or null
+    float *block_max;             // banded score-history mode: 3 rotating (Bpad, LDP/16) arrays, max of every
+    int64_t block_stride;         // 16-state block of the corresponding score row; `block_stride` floats apart
     const unsigned *band;         // banded mode: per destination tile S - first / last+1 source differing from `outside`
     const float *outside;         // banded mode: the value every transition entry outside the windows has
     int64_t T;
@@ -393,6 +395,19 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                 }
             }
         }
+        if constexpr (kBanded && kHist) {
+            // block maxima of this CTA's columns of P_0 (read back through L2 once per batch)
+            __syncthreads();
+            for (int idx = tid; idx < TM * (TN / 16); idx += kThreads) {
+                const int r = idx / (TN / 16), blk = idx % (TN / 16);
+                const int col = j0 + blk * 16;
+                if (col >= S || slot_item[r] < 0) continue;
+                const float *row = p.score0 + (row0 + r) * LDP + col;
+                float m = -INFINITY;
+                for (int e = 0; e < 16 && col + e < S; ++e) m = fmaxf(m, __ldcg(row + e));
+                p.block_max[(row0 + r) * (LDP / 16) + col / 16] = m;
+            }
+        }
         barriers += p.NJT;
         group_arrive(counter);
         group_wait(counter, barriers);
@@ -431,6 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
         for (int t = 1; t < batch_frames; ++t) {
             // three rotating buffers: a CTA that is already publishing step t+1 never
             // writes the buffer a slower CTA of the group still re-scans for step t
+            const int buf_prev = buf;
             const int buf_new = buf == 2 ? 0 : buf + 1;
             const float *P_cur = p.score0 + buf * p.score_stride;
             float *P_new = p.score0 + buf_new * p.score_stride;
@@ -451,7 +467,32 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                 }
             }
 
-            if (kBanded) {
+            if constexpr (kBanded && kHist) {
+                // Sources outside the window, score-history mode: only the VALUE max_s fl(P[s] + outside) is
+                // needed, and fl(. + outside) is monotonic, so it equals fl(max_s P[s] + outside) -- taken from
+                // the per-16-state block maxima the producers publish with the scores (window boundaries
+                // are multiples of 16).  90 loads per row instead of 1440.
+                constexpr int kRowsPerWarp = TM / (kThreads / kWarp);
+                const int nblk = (S + 15) / 16, blk_lo = k_lo / 16, blk_hi = (k_hi + 15) / 16;
+                const float *bm = p.block_max + buf_prev * p.block_stride + (row0 + warp * kRowsPerWarp) * (LDP / 16);
+                float m[kRowsPerWarp];
+#pragma unroll
+                for (int rr = 0; rr < kRowsPerWarp; ++rr) m[rr] = -INFINITY;
+                for (int b = lane; b < nblk; b += kWarp) {
+                    if (b >= blk_lo && b < blk_hi) continue;
+#pragma unroll
+                    for (int rr = 0; rr < kRowsPerWarp; ++rr)
+                        m[rr] = fmaxf(m[rr], __ldcg(bm + (int64_t)rr * (LDP / 16) + b));
+                }
+#pragma unroll
+                for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) m[rr] = fmaxf(m[rr], __shfl_xor_sync(kFullMask, m[rr], off));
+                    // (-inf when the window covers every source: never beats the window maximum)
+                    if (lane == 0) out_v[warp * kRowsPerWarp + rr] = m[rr] + outside;
+                }
+                __syncthreads();
+            } else if (kBanded) {
                 // sources outside the window: first-occurrence max of P[s] + outside, per sequence
                 // (the same single fp32 add the dense scan would do for these sources)
                 // All rows of the warp advance together so their (independent) L2 loads overlap.
@@ -602,28 +643,45 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             PROF_MARK(6)
 
             // ---- publish the new scores (finished rows are carried over), then arrive ----
-            for (int idx = tid; idx < TM * (TN / 4); idx += kThreads) {
+            for (int idx = tid; idx < TM * (TN / 4); idx += kThreads) {       // (whole warps enter or leave together)
                 const int r = idx / (TN / 4), c4 = idx % (TN / 4);
                 const int col = j0 + c4 * 4;
-                if (col >= S || slot_item[r] < 0) continue;       // padding never changes
-                const int64_t off = (row0 + r) * LDP + col;
-                const bool live = t < slot_frames[r];
-                // score-history mode: P_t of live rows also goes to the (B,T,S) history (streaming store)
-                float *hist = (kHist && live) ? p.history + ((int64_t)slot_item[r] * p.T + t) * S + col : nullptr;
-                if (col + 3 < S) {
-                    const float4 v = live ? *reinterpret_cast<const float4 *>(tile + r * TN + c4 * 4)
-                                          : __ldcg(reinterpret_cast<const float4 *>(P_cur + off));
-                    *reinterpret_cast<float4 *>(P_new + off) = v;
-                    if (kHist && live) {
-                        if (hist_vec) __stcs(reinterpret_cast<float4 *>(hist), v);
-                        else { hist[0] = v.x; hist[1] = v.y; hist[2] = v.z; hist[3] = v.w; }
+                const bool valid = col < S && slot_item[r] >= 0;              // padding never changes
+                float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                if (valid) {
+                    const int64_t off = (row0 + r) * LDP + col;
+                    const bool live = t < slot_frames[r];
+                    // score-history mode: P_t of live rows also goes to the (B,T,S) history (streaming store)
+                    float *hist = (kHist && live) ? p.history + ((int64_t)slot_item[r] * p.T + t) * S + col : nullptr;
+                    if (col + 3 < S) {
+                        v = live ? *reinterpret_cast<const float4 *>(tile + r * TN + c4 * 4)
+                                 : __ldcg(reinterpret_cast<const float4 *>(P_cur + off));
+                        *reinterpret_cast<float4 *>(P_new + off) = v;
+                        if (kHist && live) {
+                            if (hist_vec) __stcs(reinterpret_cast<float4 *>(hist), v);
+                            else { hist[0] = v.x; hist[1] = v.y; hist[2] = v.z; hist[3] = v.w; }
+                        }
+                    } else {
+                        float e[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            if (col + k < S) {
+                                e[k] = live ? tile[r * TN + c4 * 4 + k] : __ldcg(P_cur + off + k);
+                                P_new[off + k] = e[k];
+                                if (kHist && live) hist[k] = e[k];
+                            }
+                        }
+                        v = make_float4(e[0], e[1], e[2], e[3]);
                     }
-                } else {
-                    for (int e = 0; col + e < S; ++e) {
-                        const float v = live ? tile[r * TN + c4 * 4 + e] : __ldcg(P_cur + off + e);
-                        P_new[off + e] = v;
-                        if (kHist && live) hist[e] = v;
-                    }
+                }
+                if constexpr (kBanded && kHist) {
+                    // max of every 16-state block of the new row, for the next step's outside-window maximum:
+                    // the 4 lanes holding a block are adjacent (idx % 4 == c4 % 4); states >= S hold -inf
+                    float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+                    m = fmaxf(m, __shfl_xor_sync(kFullMask, m, 1));
+                    m = fmaxf(m, __shfl_xor_sync(kFullMask, m, 2));
+                    if (valid && (c4 & 3) == 0)
+                        p.block_max[buf_new * p.block_stride + (row0 + r) * (LDP / 16) + col / 16] = m;
                 }
             }
             barriers += p.NJT;
@@ -762,6 +820,8 @@ static cudaError_t launch_tiled_t(const ForwardArgs &a, cudaStream_t stream) {
     p.score_stride = a.ws.score[1] - a.ws.score[0];
     p.backptr = a.ws.backptr;
     p.history = reinterpret_cast<float *>(a.ws.backptr);
+    p.block_max = a.ws.block_max;
+    p.block_stride = pad_batch(a.B) * (tiled_ldp(a.S) / 16);
     p.posterior = a.posterior;
     p.final_state = a.ws.final_state;
     p.sync = a.ws.sync;
