@@ -173,6 +173,55 @@ TORBI_B200_API const char *torbi_b200_plan(const int32_t *batch_frames, int64_t 
  * may be NULL. */
 TORBI_B200_API int torbi_b200_last_timing(float *forward_ms, float *backtrace_ms);
 
+/*
+ * Native file I/O for the file API (from_file / from_files_to_files, core.py:211-368): the
+ * reference loads every input with torch.load and writes every result with torch.save from one
+ * Python thread (data/dataset.py:17-22, core.py:466-473).  These three host-only entries parse the
+ * torch.save container (a zip of STORED records) in C++, read the payloads with pread() straight
+ * into the caller's (pinned) batch buffer from a pool of host threads, and write int32 results in
+ * the same container format, readable by torch.load.  No CUDA call is made.
+ */
+#define TORBI_B200_PT_OK 0
+#define TORBI_B200_PT_IO_ERROR 1     /* open / read / write failed                                   */
+#define TORBI_B200_PT_NOT_A_ZIP 2    /* legacy (non-zip) torch.save file or damaged archive          */
+#define TORBI_B200_PT_UNSUPPORTED 3  /* valid file the fast path does not cover (zip64, compression,
+                                        several tensors, non-contiguous view, other pickled objects):
+                                        the caller falls back to torch.load                          */
+#define TORBI_B200_PT_F32 0
+#define TORBI_B200_PT_F16 1
+#define TORBI_B200_PT_BF16 2
+#define TORBI_B200_PT_F64 3
+#define TORBI_B200_PT_I32 4
+#define TORBI_B200_PT_I64 5
+
+typedef struct {
+    int64_t data_offset; /* byte offset in the file of the tensor's first element             */
+    int64_t nbytes;      /* bytes of the (contiguous, row-major) tensor                        */
+    int64_t shape[4];
+    int32_t ndim;        /* <= 4                                                               */
+    int32_t dtype;       /* TORBI_B200_PT_F32 ...                                              */
+    int32_t status;      /* TORBI_B200_PT_OK or why the fast path does not apply to this file  */
+    int32_t reserved;
+} torbi_b200_pt_info;
+
+/* Describe `n` torch.save files (one tensor each).  Returns the number of files whose status is
+ * not TORBI_B200_PT_OK (0 = all good), or a negative TORBI_B200_ERR_* for bad arguments.
+ * `threads` <= 0 uses every host core. */
+TORBI_B200_API int torbi_b200_pt_inspect(const char *const *paths, int64_t n, torbi_b200_pt_info *info,
+                                         int threads);
+
+/* Read the payload of file i (as described by info[i], status OK) to destinations[i] and zero the
+ * rest of its capacities[i] bytes (the zero padding of collate(), data/collate.py:26-31).  Large
+ * payloads are split across threads.  Returns the number of failed reads. */
+TORBI_B200_API int torbi_b200_pt_read(const char *const *paths, const torbi_b200_pt_info *info, int64_t n,
+                                      void *const *destinations, const int64_t *capacities, int threads);
+
+/* Write n contiguous int32 tensors (shape of tensor i = shapes[4*i .. 4*i + ndims[i])) as torch.save
+ * files.  Returns the number of failed writes. */
+TORBI_B200_API int torbi_b200_pt_write_i32(const char *const *paths, const int32_t *const *data,
+                                           const int64_t *shapes, const int32_t *ndims, int64_t n,
+                                           int threads);
+
 /* Self-test: the kernels skip logf(expf(x) + FLT_MIN) where it is the identity (every fp32 x in
  * (-64, -4], found exhaustively).  Evaluates the shortcut and the plain formula for ALL 2^32 fp32
  * bit patterns on the current device and reports how many disagree (must be 0).  Takes ~1 s;

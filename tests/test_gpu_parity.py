@@ -436,6 +436,36 @@ def test_file_drivers(tmp_path, oracle):
         want = oracle.ref_from_probabilities(torch.load(path).unsqueeze(0), None, torch.from_numpy(A), initial, True)
         assert np.array_equal(torch.load(out).numpy(), want[0])
 
+    # the DataLoader route of the reference instead of the native reader / writer: same files
+    import os
+    for out in outputs:
+        out.unlink()
+    os.environ['TORBI_B200_NATIVE_IO'] = '0'
+    try:
+        torbi_b200.from_files_to_files(
+            files, outputs, tmp_path / 'transition.pt', tmp_path / 'initial.pt', log_probs=True, gpu=0)
+    finally:
+        del os.environ['TORBI_B200_NATIVE_IO']
+    for path, out, f in zip(files, outputs, lengths):
+        want = oracle.ref_from_probabilities(torch.load(path).unsqueeze(0), None, torch.from_numpy(A), initial, True)
+        assert np.array_equal(torch.load(out).numpy(), want[0])
+
+    # a half-precision and a legacy-format input in the batch: per-batch / per-file fallbacks
+    odd = [tmp_path / 'half.pt', tmp_path / 'legacy.pt']
+    torch.save(torch.load(files[0]).half(), odd[0])
+    torch.save(torch.load(files[2]), odd[1], _use_new_zipfile_serialization=False)
+    odd_out = [tmp_path / 'half.out.pt', tmp_path / 'legacy.out.pt']
+    torbi_b200.from_files_to_files(
+        [files[1], odd[1]], [outputs[1], odd_out[1]], tmp_path / 'transition.pt', tmp_path / 'initial.pt',
+        log_probs=True, gpu=0)
+    assert torch.equal(torch.load(odd_out[1]), torch.load(outputs[2]))
+    torbi_b200.from_files_to_files(
+        [files[1], odd[0]], [outputs[1], odd_out[0]], tmp_path / 'transition.pt', tmp_path / 'initial.pt',
+        log_probs=True, gpu=0)
+    want = oracle.ref_from_probabilities(
+        torch.load(odd[0]).unsqueeze(0), None, torch.from_numpy(A), initial, True)
+    assert np.array_equal(torch.load(odd_out[0]).numpy(), want[0])
+
     # from_file: transition logged WITHOUT tiny (core.py:247-250), shape (1, frames)
     got = torbi_b200.from_file(files[0], tmp_path / 'transition.pt', tmp_path / 'initial.pt',
                                log_probs=True, gpu=0)

@@ -243,3 +243,66 @@ def test_product_never_imports_the_oracle():
         if path.suffix in ('.py', '.cu', '.cuh', '.h'):
             text = path.read_text()
             assert 'oracle' not in text.lower(), path
+
+
+def test_native_file_reader_and_writer(tmp_path):
+    """csrc/ptfile.cpp against torch.save / torch.load: plain files through the fast path, views,
+    other dtypes, legacy and non-tensor files through the per-file fallback; written files load
+    back with torch.load (weights_only and mmap included)."""
+    from torbi_b200.data import native
+    rng = torch.Generator().manual_seed(3)
+    lengths = [7, 1, 12, 5]
+    tensors = [torch.randn((f, 24), generator=rng) for f in lengths]
+    files = []
+    for i, x in enumerate(tensors):
+        files.append(tmp_path / f'{i}.pt')
+        torch.save(x, files[-1])
+    infos = native.inspect(files)
+    assert [info.status for info in infos] == [0] * 4
+    assert [tuple(info.shape[:info.ndim]) for info in infos] == [(f, 24) for f in lengths]
+    assert all(info.dtype == _ffi.PT_F32 and info.nbytes == f * 24 * 4 for info, f in zip(infos, lengths))
+
+    observation, frames = native.load_batch(files, threads=3)
+    assert frames.tolist() == lengths and observation.shape == (4, 12, 24)
+    for i, x in enumerate(tensors):
+        assert torch.equal(observation[i, :lengths[i]], x)
+        assert not observation[i, lengths[i]:].any()                       # zero padding like collate()
+    # identical to the reference route (Dataset + collate)
+    want = torbi_b200.data.collate([(torch.load(f), f) for f in files])[0]
+    assert torch.equal(observation, want)
+    # into a caller-provided flat buffer
+    flat = torch.full((4 * 12 * 24 + 5,), 7.)
+    again, _ = native.load_batch(files, out=flat)
+    assert again.data_ptr() == flat.data_ptr() and torch.equal(again, want)
+
+    # files outside the fast path fall back one by one: a view with an offset is still native,
+    # transposed / legacy / wrapped objects are not
+    base = torch.randn((10, 24), generator=rng)
+    torch.save(base[2:7], tmp_path / 'view.pt')
+    torch.save(base.t().contiguous().t(), tmp_path / 'strided.pt')
+    torch.save(base, tmp_path / 'legacy.pt', _use_new_zipfile_serialization=False)
+    torch.save({'x': base}, tmp_path / 'dict.pt')
+    status = [info.status for info in native.inspect(
+        [tmp_path / 'view.pt', tmp_path / 'strided.pt', tmp_path / 'legacy.pt', tmp_path / 'dict.pt',
+         tmp_path / 'missing.pt'])]
+    assert status == [0, 3, 2, 3, 1]
+    mixed, frames = native.load_batch([tmp_path / 'view.pt', tmp_path / 'strided.pt', tmp_path / 'legacy.pt'])
+    assert frames.tolist() == [5, 10, 10]
+    assert torch.equal(mixed[0, :5], base[2:7]) and torch.equal(mixed[1], base) and torch.equal(mixed[2], base)
+    # other dtypes / ranks: the caller gets None and uses the generic collate
+    torch.save(base.half(), tmp_path / 'half.pt')
+    assert native.inspect([tmp_path / 'half.pt'])[0].dtype == _ffi.PT_F16
+    assert native.load_batch([files[0], tmp_path / 'half.pt']) is None
+
+    outputs = [torch.randint(0, 1440, (n,), dtype=torch.int32, generator=rng) for n in (500, 1, 0, 70000)]
+    outputs.append(torch.randint(0, 9, (1, 77), dtype=torch.int32, generator=rng))
+    paths = [tmp_path / f'out{i}.pt' for i in range(len(outputs))]
+    native.save_int32(outputs, paths, threads=2)
+    for tensor, path in zip(outputs, paths):
+        for kwargs in ({}, {'weights_only': True}, {'weights_only': True, 'mmap': True}):
+            back = torch.load(path, **kwargs)
+            assert back.dtype == torch.int32 and back.shape == tensor.shape and torch.equal(back, tensor)
+    with pytest.raises(ValueError):
+        native.save_int32([torch.zeros(3)], [tmp_path / 'bad.pt'])
+    with pytest.raises(OSError):
+        native.save_int32([outputs[0]], [tmp_path / 'no_such_dir' / 'x.pt'])

@@ -57,6 +57,24 @@ SIGNATURES = {
     'torbi_b200_plan': (ctypes.c_char_p, [_p, _i64, _i64, _i64, ctypes.c_uint32, ctypes.c_int]),
 }
 
+
+
+class PtInfo(ctypes.Structure):
+    """torbi_b200_pt_info of include/torbi_b200.h"""
+    _fields_ = [('data_offset', ctypes.c_int64), ('nbytes', ctypes.c_int64), ('shape', ctypes.c_int64 * 4),
+                ('ndim', ctypes.c_int32), ('dtype', ctypes.c_int32), ('status', ctypes.c_int32),
+                ('reserved', ctypes.c_int32)]
+
+
+PT_OK = 0
+PT_F32, PT_F16, PT_BF16, PT_F64, PT_I32, PT_I64 = range(6)
+
+SIGNATURES.update({
+    'torbi_b200_pt_inspect': (ctypes.c_int, [_p, _i64, _p, ctypes.c_int]),
+    'torbi_b200_pt_read': (ctypes.c_int, [_p, _p, _i64, _p, _p, ctypes.c_int]),
+    'torbi_b200_pt_write_i32': (ctypes.c_int, [_p, _p, _p, _p, _i64, ctypes.c_int]),
+})
+
 _lib = None
 
 

@@ -381,19 +381,34 @@ def from_files_to_files(
     # batch small.  The reference batches in the given order (loader.py:19-25).
     sizes = [os.path.getsize(file) for file in input_files]
 
+    # Whole files, in-process loading: the native pipeline (C++ reader / writer threads, pinned
+    # ring of batch buffers).  Chunked decoding (MIN_CHUNK_SIZE) and worker-process loaders keep
+    # the DataLoader route of the reference.
+    native = torbi_b200.MIN_CHUNK_SIZE is None and torbi_b200.NUM_WORKERS == 0 and \
+        os.environ.get('TORBI_B200_NATIVE_IO', '1') != '0'
+
+    def run(files, file_sizes, device, progress, io_threads):
+        if native:
+            _from_files_native(files, file_sizes, mapping, transition, initial, log_probs, device,
+                               progress, io_threads)
+        else:
+            from_dataloader(
+                dataloader=torbi_b200.data.loader(
+                    files, batch_sampler=size_bucketed_batches(file_sizes, torbi_b200.BATCH_SIZE),
+                    collate_fn=_pinned_collate()),
+                output_files=mapping,
+                transition=transition,
+                initial=initial,
+                log_probs=log_probs,
+                gpu=device,
+                num_threads=num_threads,
+                progress=progress,
+                prefetch=2,
+                save_workers=4)
+
+    cores = os.cpu_count() or 1
     if len(devices) == 1:
-        from_dataloader(
-            dataloader=torbi_b200.data.loader(
-                input_files, batch_sampler=size_bucketed_batches(sizes, torbi_b200.BATCH_SIZE),
-                collate_fn=_pinned_collate()),
-            output_files=mapping,
-            transition=transition,
-            initial=initial,
-            log_probs=log_probs,
-            gpu=devices[0],
-            num_threads=num_threads,
-            prefetch=2,
-            save_workers=4)
+        run(input_files, sizes, devices[0], True, cores)
         return
 
     shards = lpt_shards(sizes, len(devices))
@@ -401,21 +416,8 @@ def from_files_to_files(
 
     def work(k, items):
         try:
-            shard_files = [input_files[i] for i in items]
-            from_dataloader(
-                dataloader=torbi_b200.data.loader(
-                    shard_files, batch_sampler=size_bucketed_batches(
-                        [sizes[i] for i in items], torbi_b200.BATCH_SIZE),
-                    collate_fn=_pinned_collate()),
-                output_files=mapping,
-                transition=transition,
-                initial=initial,
-                log_probs=log_probs,
-                gpu=devices[k],
-                num_threads=num_threads,
-                progress=(k == 0),
-                prefetch=2,
-                save_workers=4)
+            run([input_files[i] for i in items], [sizes[i] for i in items], devices[k], k == 0,
+                max(2, cores // len(devices)))
         except BaseException as error:  # noqa: BLE001
             errors.append(error)
 
@@ -426,6 +428,86 @@ def from_files_to_files(
         thread.join()
     if errors:
         raise errors[0]
+
+
+def _from_files_native(input_files, sizes, mapping, transition, initial, log_probs, device, progress,
+                       io_threads, batch_bytes=1 << 29, depth=2):
+    """The file pipeline of one GPU.  A loader thread fills a ring of `depth + 1` pinned batch
+    buffers through the native reader (csrc/ptfile.cpp: central directory + pickle parsed in
+    C++, payloads pread() straight into the padded batch by `io_threads` host threads) while
+    the GPU decodes the previous batch; results are written by the native writer on a third
+    thread.  Per file the work is the reference's (torch.load -> pad -> decode -> torch.save of
+    an int32 (frames,) tensor, core.py:376-463), only the plumbing differs."""
+    from .data import native as native_io
+
+    batches = size_bucketed_batches(sizes, torbi_b200.BATCH_SIZE, max_padded_bytes=batch_bytes)
+    if not batches:
+        return
+    # file size bounds the payload, the first file of a batch is its largest
+    numel = max(len(batch) * int(sizes[batch[0]]) for batch in batches) // 4 + 1
+    pin = torch.cuda.is_available()
+    free: queue.Queue = queue.Queue()
+    for _ in range(depth + 1):
+        free.put(torch.empty(numel, dtype=torch.float32, pin_memory=pin))
+    ready: queue.Queue = queue.Queue(maxsize=depth)
+    done = object()
+
+    def produce():
+        try:
+            for batch in batches:
+                files = [input_files[i] for i in batch]
+                buffer = free.get()
+                loaded = native_io.load_batch(files, threads=io_threads, out=buffer)
+                if loaded is None:
+                    # mixed dtypes / widths: the reference's own collate (file dtype kept, cast later)
+                    dataset = torbi_b200.data.Dataset(files)
+                    observation, batch_frames, _, _ = torbi_b200.data.collate(
+                        [dataset[i] for i in range(len(files))], pin_memory=pin)
+                    loaded = (observation, batch_frames)
+                ready.put((loaded[0], loaded[1], files, buffer))
+            ready.put(done)
+        except BaseException as error:  # noqa: BLE001 - re-raised by the consumer
+            ready.put(error)
+
+    threading.Thread(target=produce, daemon=True).start()
+
+    if transition is not None:
+        log_transition = transition if log_probs else torch.log(transition)
+        banded = _is_banded(log_transition.to(torch.float32))
+    else:
+        banded = None
+    bar = _progress(len(input_files)) if progress else None
+    saver = concurrent.futures.ThreadPoolExecutor(1)
+    pending = []
+    try:
+        while True:
+            item = ready.get()
+            if item is done:
+                break
+            if isinstance(item, BaseException):
+                raise item
+            observation, batch_frames, files, buffer = item
+            indices = from_probabilities(
+                observation=observation,
+                batch_frames=batch_frames,
+                transition=transition,
+                initial=initial,
+                log_probs=log_probs,
+                gpu=device,
+                banded=(banded and len(files) >= 32) if banded is not None else None)
+            indices = indices.cpu()            # also orders the host->device copy before the buffer is reused
+            free.put(buffer)
+            rows = [indices[i, :int(frames)] for i, frames in enumerate(batch_frames)]      # core.py:452-457
+            pending.append(saver.submit(native_io.save_int32, rows, [mapping[file] for file in files],
+                                        io_threads))
+            if bar is not None:
+                bar.update(len(files))
+        for future in pending:
+            future.result()
+    finally:
+        saver.shutdown(wait=True)
+        if bar is not None:
+            bar.close()
 
 
 ###############################################################################
