@@ -23,7 +23,11 @@ for (B, T, S) in [(5, 6, 200), (70, 4, 96), (3, 5, 333)]:
     frames[0] = T
     want = oracle.c_decode(obs, frames, A, init)
     for name, flag in [('generic', _ffi.FORCE_GENERIC), ('tiled64', _ffi.TILE_ROWS_64), ('tiled32', _ffi.TILE_ROWS_32),
-                       ('tiled16', _ffi.TILE_ROWS_16), ('wide', _ffi.FORCE_WIDE)]:
+                       ('tiled16', _ffi.TILE_ROWS_16), ('wide', _ffi.FORCE_WIDE),
+                       ('tiled64 backpointers', _ffi.TILE_ROWS_64 | _ffi.BACKPOINTERS),
+                       ('tiled16 backpointers', _ffi.TILE_ROWS_16 | _ffi.BACKPOINTERS),
+                       ('banded', _ffi.BANDED | _ffi.TILE_ROWS_64), ('banded16', _ffi.BANDED | _ffi.TILE_ROWS_16),
+                       ('banded backpointers', _ffi.BANDED | _ffi.BACKPOINTERS)]:
         got = torbi_b200.decode(torch.from_numpy(obs).cuda(), torch.from_numpy(frames), torch.from_numpy(A).cuda(),
                                 torch.from_numpy(init).cuda(), flags=flag | _ffi.EPS_FLOOR)
         torch.cuda.synchronize()

@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
     }
     __syncthreads();
     unsigned stage_counter = 0;      // pipeline stages consumed so far by this thread (slot = counter % NSTAGE)
+    unsigned empty_parity = 0;       // bit k: parity of the next phase of empty_bar[k] this thread will wait for
     __shared__ int ready_shared;
     int ready = p.frames_ready ? 0 : 0x7fffffff;    // frames of `observation` known to be in HBM
     // the host entry copies the batch in T-chunks while this kernel runs: block
@@ -332,24 +333,30 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
     // Pipeline stages this CTA runs per step.  Dense: all of them.  Banded: only the window
     // outside which every transition entry of this destination tile equals *p.outside (the
     // device-side analysis, analyze_band_kernel, guarantees it for any matrix).
+    // The window is kept at chunk (32-state) granularity: whole stages are staged, but the chunks of
+    // the first / last stage that lie outside the window are skipped by the math.
     int s_lo = 0, s_hi = LDP / KS;
+    int c_lo = 0, c_hi = LDP / KC;
     float outside = 0.f;
     if (kBanded) {
         const int lo = S - (int)p.band[jt], hi = (int)p.band[p.NJT + jt];
-        s_lo = lo / KS;
-        s_hi = (hi + KS - 1) / KS;
-        if (lo >= hi) s_lo = s_hi = 0;
+        c_lo = lo / KC;
+        c_hi = (hi + KC - 1) / KC;
+        if (lo >= hi) c_lo = c_hi = 0;
+        s_lo = c_lo / (KS / KC);
+        s_hi = (c_hi + KS / KC - 1) / (KS / KC);
         outside = *p.outside;
     }
     const int nstages = s_hi - s_lo;
-    const int k_lo = s_lo * KS, k_hi = min(s_hi * KS, S);
+    const int stage_base = s_lo * KS;                             // first source state staged
+    const int k_lo = c_lo * KC, k_hi = min(c_hi * KC, S);         // sources covered by the dense loop
     const bool obs_vec = (S % 4) == 0 && (reinterpret_cast<uintptr_t>(p.observation) & 15) == 0;
     const bool bp_vec = (S % 8) == 0;
     const bool hist_vec = (S % 4) == 0;
     // loader mapping (see load_stage)
     const int ld_c4 = tid % (KS / 4), ld_r0 = tid / (KS / 4);
     const int ld_smem = ld_r0 * LDS_ + ld_c4 * 4;
-    const float *ld_A = p.transition + (int64_t)(j0 + ld_r0) * LDP + ld_c4 * 4 + k_lo;
+    const float *ld_A = p.transition + (int64_t)(j0 + ld_r0) * LDP + ld_c4 * 4 + stage_base;
     const int64_t ld_stride10 = (int64_t)10 * LDP;
 
     unsigned *queue_head = p.sync + p.NG * 32;       // batches are handed out longest first
@@ -451,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             const float *P_cur = p.score0 + buf * p.score_stride;
             float *P_new = p.score0 + buf_new * p.score_stride;
             buf = buf_new;
-            const float *ld_P = P_cur + (row0 + ld_r0) * LDP + ld_c4 * 4 + k_lo;
+            const float *ld_P = P_cur + (row0 + ld_r0) * LDP + ld_c4 * 4 + stage_base;
 
             // the emission tile and the transition rows of stages 0 / 1 were prefetched before
             // the exchange wait (prefetch_step); only the score rows are left
@@ -572,11 +579,16 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                     if (refill && ch == 1) {
                         // Refill the slot the previous stage used, one chunk into this stage: by now every
                         // warp has (almost surely) released it, so the wait does not couple the warps.
-                        const unsigned uses = (stage_counter + 2) / NSTAGE;     // earlier uses of that slot
-                        if (uses > 0) mbar_wait(empty_bar + rslot, (uses - 1) & 1);
+                        // (s == 0: the slot's last readers belong to the previous step, behind CTA barriers)
+                        if (s > 0) {
+                            mbar_wait(empty_bar + rslot, (empty_parity >> rslot) & 1u);
+                            empty_parity ^= 1u << rslot;
+                        }
                         load_stage<TM>(refill_dst, refill_A, refill_P, ld_stride10, ld_r0);
                         cp_async_arrive(full_bar + rslot);
                     }
+                    const int chunk = (s_lo + s) * (KS / KC) + ch;
+                    if (kBanded && (chunk < c_lo || chunk >= c_hi)) continue;     // outside the window (CTA-uniform)
                     float acc[M][N];
 #pragma unroll
                     for (int k = 0; k < KC; k += 4) {
@@ -598,7 +610,6 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                                 acc[i][c] = fmaxf(fmaxf(fmaxf(fmaxf(a0, lo(v0)), hi(v0)), lo(v1)), hi(v1));
                             }
                     }
-                    const int chunk = (s_lo + s) * (KS / KC) + ch;
 #pragma unroll
                     for (int i = 0; i < M; ++i)
 #pragma unroll
@@ -607,8 +618,12 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                             cur[i][c] = acc[i][c];
                         }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty_bar + slot);          // this warp is done with the slot
+                // this warp is done with the slot; signalled only when a refill (during the next stage,
+                // for stage s + 3) is going to wait for it, so every barrier phase has its waiters
+                if (s + 3 < nstages) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty_bar + slot);
+                }
             }
             // The emission tile was copied with the step's first stage, whose full-barrier every thread
             // has passed.  Without any stage (banded, empty window) or with plain stores (unaligned
