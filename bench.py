@@ -53,9 +53,10 @@ def parse_args():
     parser.add_argument('--cpu-seconds', type=float, default=None,
                         help='CPU work per reference step / cpu_baseline sample (default: sized automatically)')
     parser.add_argument('--no-cpu-baseline', action='store_true')
-    parser.add_argument('--kernel', default='auto', choices=['auto', 'generic', 'tiled', 'wide'])
+    parser.add_argument('--kernel', default='auto', choices=['auto', 'generic', 'tiled', 'wide', 'split'])
     parser.add_argument('--tile-rows', type=int, default=0, choices=[0, 16, 32, 64])
     parser.add_argument('--ws', action='store_true', help='warp-specialised tiled kernel')
+    parser.add_argument('--split-streamed', action='store_true', help='split kernel: streamed 16 x 40 tiles')
     parser.add_argument('--backpointers', action='store_true',
                         help="tiled kernel in backpointer mode (uint16 trellis) instead of score history + recomputed backtrace")
     parser.add_argument('--banded', action='store_true', help='exact banded-transition fast path (not the contract metric)')
@@ -269,7 +270,8 @@ def bench_graft(args):
     B, T, S = args.batch, args.frames, args.states
     obs, frames, A, init = make_workload(args, device, 1234 + rank)
     flags = _ffi.EPS_FLOOR | _ffi.TIME_KERNELS
-    flags |= {'auto': 0, 'generic': _ffi.FORCE_GENERIC, 'tiled': _ffi.FORCE_TILED, 'wide': _ffi.FORCE_WIDE}[args.kernel]
+    flags |= {'auto': 0, 'generic': _ffi.FORCE_GENERIC, 'tiled': _ffi.FORCE_TILED, 'wide': _ffi.FORCE_WIDE,
+              'split': _ffi.FORCE_SPLIT}[args.kernel]
     flags |= {0: 0, 16: _ffi.TILE_ROWS_16, 32: _ffi.TILE_ROWS_32, 64: _ffi.TILE_ROWS_64}[args.tile_rows]
     if args.ws:
         flags |= _ffi.TILED_WS
@@ -277,6 +279,8 @@ def bench_graft(args):
         flags |= _ffi.BANDED
     if args.backpointers:
         flags |= _ffi.BACKPOINTERS
+    if args.split_streamed:
+        flags |= _ffi.SPLIT_STREAMED
     timesteps_per_step = int(frames.sum())
 
     fwd_ms, back_ms = [], []

@@ -78,6 +78,13 @@ extern "C" {
  * (viterbi.cpp:91-104); slower, half the workspace.  Pass the same flag to
  * torbi_b200_workspace_bytes.  The wide and generic kernels always store backpointers. */
 #define TORBI_B200_BACKPOINTERS (1u << 16)
+/* force the split-K small-tile kernel (32 sequences x 20 states per CTA with the transition block
+ * resident in shared memory, or 16 x 40 streamed; score-history mode): the decomposition for batches
+ * too small to fill the chip with 64 x 80 tiles */
+#define TORBI_B200_FORCE_SPLIT (1u << 17)
+/* with the split kernel: stream the transition block (16 x 40 tiles) even where the resident
+ * 32 x 20 shape would fit (states <= 1536); tests / tuning */
+#define TORBI_B200_SPLIT_STREAMED (1u << 18)
 /* use the warp-specialised variant of the tiled kernel (64-row batches, S % 8 == 0) */
 #define TORBI_B200_TILED_WS (1u << 14)
 

@@ -17,7 +17,9 @@ KERNELS = {'auto': 0, 'generic': _ffi.FORCE_GENERIC, 'tiled16': _ffi.TILE_ROWS_1
            'banded16': _ffi.BANDED | _ffi.TILE_ROWS_16,
            # the tiled kernel's backpointer mode (default is score history + recomputed backtrace)
            'tiled64bp': _ffi.TILE_ROWS_64 | _ffi.BACKPOINTERS, 'tiled16bp': _ffi.TILE_ROWS_16 | _ffi.BACKPOINTERS,
-           'tiled32bp': _ffi.TILE_ROWS_32 | _ffi.BACKPOINTERS, 'bandedbp': _ffi.BANDED | _ffi.BACKPOINTERS}
+           'tiled32bp': _ffi.TILE_ROWS_32 | _ffi.BACKPOINTERS, 'bandedbp': _ffi.BANDED | _ffi.BACKPOINTERS,
+           # split-K 16 x 40 tiles (small and mid-size batches)
+           'split': _ffi.FORCE_SPLIT, 'split_streamed': _ffi.FORCE_SPLIT | _ffi.SPLIT_STREAMED}
 
 
 def bits(a):

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_flag_values_match_header():
     header = (ROOT / 'include' / 'torbi_b200.h').read_text()
     for name in ('OBS_IS_PROBABILITY', 'EPS_FLOOR', 'FORCE_GENERIC', 'FORCE_TILED', 'FORCE_WIDE', 'TIME_KERNELS',
-                 'TILED_WS', 'BANDED', 'BACKPOINTERS'):
+                 'TILED_WS', 'BANDED', 'BACKPOINTERS', 'FORCE_SPLIT', 'SPLIT_STREAMED'):
         shift = int(re.search(rf'#define TORBI_B200_{name} \(1u << (\d+)\)', header).group(1))
         assert getattr(_ffi, name) == 1 << shift
     for name, value in (('TILE_ROWS_16', 1), ('TILE_ROWS_32', 2), ('TILE_ROWS_64', 3)):
@@ -64,10 +64,15 @@ def test_kernel_plan_host_logic():
     full = [2000] * 512
     assert plan(full, 2000, 1440) == 'forward_tiled'                       # the headline shape: 64-row tiles
     assert plan([2000] * 256, 2000, 1440) == 'forward_tiled_32'            # 8 groups need 8 batches
-    assert plan([2000] * 128, 2000, 1440) == 'forward_tiled_16'
+    assert plan([2000] * 128, 2000, 1440) == 'forward_split'               # too few for 64 x 80 tiles: split-K 32 x 20
+    assert plan([2000] * 64, 2000, 1440) == 'forward_split'                # the per-GPU share of 512 over 8 GPUs
+    assert plan([2000] * 128, 2000, 1440, _ffi.BACKPOINTERS) == 'forward_tiled_16'   # (no split kernel in that mode)
     assert plan([2000], 2000, 1440) == 'forward_wide'                      # config 1
     assert plan([1000000], 1000000, 4096) == 'forward_wide'                # config 5
-    assert plan([2000] * 16, 2000, 1440) == 'forward_wide'
+    assert plan([2000] * 8, 2000, 1440) == 'forward_wide'
+    assert plan([2000] * 16, 2000, 1440) == 'forward_split'
+    assert plan(full, 2000, 1440, _ffi.FORCE_SPLIT) == 'forward_split'
+    assert plan(full, 2000, 1440, _ffi.FORCE_SPLIT | _ffi.BACKPOINTERS) is None
     assert plan(full, 2000, 1440, _ffi.BANDED) == 'forward_tiled_banded'
     assert plan(full, 2000, 1440, _ffi.TILED_WS) == 'forward_tiled_ws'
     assert plan(full, 2000, 1440, _ffi.FORCE_GENERIC) == 'forward_generic'
@@ -75,7 +80,9 @@ def test_kernel_plan_host_logic():
     # ragged, heavy tailed: smaller tiles shorten the critical path of the longest items
     rng = np.random.default_rng(1234)
     ragged = np.exp(rng.uniform(np.log(200), np.log(20000), size=256)).round().astype(np.int32)
-    assert plan(ragged, 20000, 1440) == 'forward_tiled_16'
+    assert plan(ragged, 20000, 1440) == 'forward_split'
+    assert plan(ragged, 20000, 1440, _ffi.BACKPOINTERS) == 'forward_tiled_16'
+    assert plan(ragged, 20000, 1440, _ffi.BANDED) == 'forward_tiled_banded_16'
     # more destination tiles than SMs: no tiled kernel; 20000 states still fit the wide one
     assert plan([4, 4], 4, 20000) == 'forward_wide'
     assert plan([4, 4], 4, 20000, _ffi.FORCE_TILED) is None and 'tiled kernel' in _ffi.last_error()

@@ -31,6 +31,8 @@ TILE_ROWS_64 = 3 << 12
 TILED_WS = 1 << 14
 BANDED = 1 << 15
 BACKPOINTERS = 1 << 16
+FORCE_SPLIT = 1 << 17
+SPLIT_STREAMED = 1 << 18
 
 ABI_VERSION = 1
 

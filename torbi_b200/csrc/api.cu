@@ -141,7 +141,7 @@ size_t torbi_b200_workspace_bytes(int64_t B, int64_t T, int64_t S, uint32_t flag
 
 namespace {
 
-enum Choice { kGeneric, kTiled, kWide };
+enum Choice { kGeneric, kTiled, kWide, kSplit };
 
 // Kernel selection: estimated time of the batch-tiled and the wide decomposition for this
 // length profile (longest-first `order`), unless a flag forces one.  Also fixes a.tile_rows.
@@ -155,10 +155,22 @@ int choose_kernel(ForwardArgs &a, const int32_t *batch_frames, const std::vector
     if (flags & TORBI_B200_TILE_ROWS_MASK)
         a.tile_rows = 16 << (((flags & TORBI_B200_TILE_ROWS_MASK) >> 12) - 1);
     const bool can_tile = forward_tiled_supported(a), can_wide = forward_wide_supported(a);
+    // the split-K small-tile kernel exists in score-history mode only, dense transitions only
+    const bool can_split = forward_split_supported(a) && workspace_has_history(flags) &&
+                           !(flags & (TORBI_B200_BANDED | TORBI_B200_TILED_WS));
     Choice choice = kGeneric;
-    if (can_tile) choice = kTiled;
-    if (can_wide && (!can_tile || wide_estimate_seconds(sorted.data(), B, S, a.sm_count) < tiled_seconds))
-        choice = kWide;
+    double best_seconds = 1e300;
+    if (can_tile) { choice = kTiled; best_seconds = tiled_seconds; }
+    if (can_split) {
+        const double seconds = split_estimate_seconds(sorted.data(), B, S, a.sm_count);
+        if (seconds < best_seconds) { choice = kSplit; best_seconds = seconds; }
+    }
+    if (can_wide && wide_estimate_seconds(sorted.data(), B, S, a.sm_count) < best_seconds) choice = kWide;
+    if (flags & TORBI_B200_FORCE_SPLIT) {
+        if (!can_split)
+            return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "split kernel does not support this shape / these flags");
+        choice = kSplit;
+    }
     if (flags & (TORBI_B200_FORCE_TILED | TORBI_B200_TILE_ROWS_MASK | TORBI_B200_BANDED)) {
         if (!can_tile) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "tiled kernel does not support this shape");
         choice = kTiled;
@@ -181,6 +193,7 @@ const char *kernel_name(const ForwardArgs &a, Choice choice, uint32_t flags) {
             return a.tile_rows == 64 ? "forward_tiled_banded" : a.tile_rows == 32 ? "forward_tiled_banded_32" : "forward_tiled_banded_16";
         return a.tile_rows == 64 ? "forward_tiled" : a.tile_rows == 32 ? "forward_tiled_32" : "forward_tiled_16";
     }
+    if (choice == kSplit) return "forward_split";
     return choice == kWide ? "forward_wide" : "forward_generic";
 }
 
@@ -265,6 +278,9 @@ int decode_device(const float *observation, const int32_t *batch_frames,
         e = launch_forward_generic(a, stream);
     } else if (choice == kWide) {
         e = launch_forward_wide(a, stream);
+    } else if (choice == kSplit) {
+        history = true;
+        e = launch_forward_split(a, stream);
     } else if (!std::strcmp(g_last_kernel, "forward_tiled_ws")) {
         e = launch_forward_tiled_ws(a, stream);
     } else if (workspace_has_history(flags)) {

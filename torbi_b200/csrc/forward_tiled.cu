@@ -887,7 +887,7 @@ static cudaError_t launch_tiled_m(const ForwardArgs &a, cudaStream_t stream) {
 
 #if !TORBI_TILED_HIST
 // Relative cost of one timestep of a TM-row batch (measured on the B200, S = 1440).
-static double step_cost(int tm) { return tm == 64 ? 1.0 : tm == 32 ? 0.57 : 0.46; }
+static double step_cost(int tm) { return tm == 64 ? 1.0 : tm == 32 ? 0.61 : 0.53; }
 
 // Batch height for this call: simulate longest-first list scheduling of the
 // length-sorted batches over the CTA groups for TM = 64 / 32 / 16 and take the
@@ -909,8 +909,9 @@ int tiled_choose_rows(const int32_t *frames_sorted, int64_t B, int64_t S, int sm
         const double makespan = *std::max_element(load.begin(), load.end());
         if (makespan < best * 0.97) { best = makespan; best_tm = tm; }   // prefer the taller tile on near-ties
     }
-    // one step of a 64-row batch takes 86 us at S = 1440 (49 / 40 us for 32 / 16 rows) and scales with the K loop
-    if (seconds) *seconds = best * 86.0e-6 * (double)tiled_ldp(S) / 1440.0;
+    // one step of a 64-row batch takes 69 us at S = 1440 in score-history mode (42 / 37 us for 32 / 16 rows;
+    // backpointer mode 86 / 49 / 40 us) and scales with the K loop
+    if (seconds) *seconds = best * 69.0e-6 * (double)tiled_ldp(S) / 1440.0;
     return best_tm;
 }
 

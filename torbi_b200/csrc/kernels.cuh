@@ -34,6 +34,12 @@ int tiled_choose_rows(const int32_t *frames_sorted, int64_t B, int64_t S, int sm
                       double *seconds);
 cudaError_t launch_pad_transition(const ForwardArgs &a, cudaStream_t stream);
 
+// forward_split.cu -- split-K small tiles (32 x 20 with the transition block resident in shared memory,
+// or 16 x 40 streamed) for batches too small to fill the chip with 64 x 80 tiles (score-history mode only)
+bool forward_split_supported(const ForwardArgs &a);
+double split_estimate_seconds(const int32_t *frames_sorted, int64_t B, int64_t S, int sm_count);
+cudaError_t launch_forward_split(const ForwardArgs &a, cudaStream_t stream);
+
 // forward_tiled_ws.cu -- warp-specialised variant of the tiled kernel for 64-row batches
 bool forward_tiled_ws_supported(const ForwardArgs &a);
 cudaError_t launch_forward_tiled_ws(const ForwardArgs &a, cudaStream_t stream);
