@@ -8,6 +8,8 @@ A "step" is one pass of the hot path over one batch of synthetic input.  For
 N > 1 the driver launches one process per GPU (torchrun); every rank decodes its
 own batch of 512 sequences (weak scaling: the path shards over independent
 sequences, no data-path collective) and rank 0 prints ONE JSON line.
+`--scaling strong` (not what the driver runs) instead splits ONE batch of 512 over the N
+ranks -- 512 / N sequences per GPU, decoded by the split-K small-tile kernel.
 
   value      whole-job timesteps/s with inputs resident in HBM, CUDA events, max over ranks
   e2e        the same through the C ABI host entry (torbi_b200_decode_host): pinned host
@@ -49,6 +51,8 @@ def parse_args():
     parser.add_argument('--batch', type=int, default=512)
     parser.add_argument('--frames', type=int, default=2000)
     parser.add_argument('--states', type=int, default=1440)
+    parser.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                        help='strong: --batch is the GLOBAL batch, split evenly over the ranks')
     parser.add_argument('--no-e2e', action='store_true')
     parser.add_argument('--cpu-seconds', type=float, default=None,
                         help='CPU work per reference step / cpu_baseline sample (default: sized automatically)')
@@ -267,6 +271,10 @@ def bench_graft(args):
         torch.cuda.synchronize()
 
     lib = _ffi.library()
+    if args.scaling == 'strong':
+        if args.batch % world:
+            raise SystemExit('--scaling strong needs --batch divisible by the number of ranks')
+        args.batch //= world                       # per-rank share from here on
     B, T, S = args.batch, args.frames, args.states
     obs, frames, A, init = make_workload(args, device, 1234 + rank)
     flags = _ffi.EPS_FLOOR | _ffi.TIME_KERNELS
@@ -358,7 +366,7 @@ def bench_graft(args):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(args, world),
             'e2e': None if e2e_ms is None else {
                 'value': total / (e2e_max * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
