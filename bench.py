@@ -263,7 +263,19 @@ def bench_graft(args):
     torch.cuda.set_device(local)
     device = torch.device(f'cuda:{local}')
     if world > 1:
-        dist.init_process_group('nccl', device_id=device)
+        # NCCL may print its version banner on stdout (NCCL_DEBUG=VERSION on some boxes); the contract is
+        # ONE JSON line there, so stdout points at stderr while the communicator comes up
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     def barrier():
         if world > 1:
