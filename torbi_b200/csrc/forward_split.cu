@@ -21,12 +21,18 @@
 //     is what bounds the streaming shape (measured 4.4 TB/s).  Needs S <= 1536 (shared memory).
 //   * 16 sequences x 40 states, transition block STREAMED with the scores: any S <= 40 x #SM.
 //
+// In the resident shape every warp streams ITS eighth of the score columns through a private
+// double buffer (cp.async groups + __syncwarp; no barrier couples the warps inside a step), in
+// stages of 8 k-steps that run without a branch so the operand loads of the next k-step are
+// scheduled under the math of the current one (worth 7 %).  The streamed shape uses a 6-stage
+// mbarrier ring shared by the CTA, like forward_tiled.cu.
+//
 // Everything else follows forward_tiled.cu: persistent cooperative grid, groups of
-// NJT = ceil(S / 40) CTAs per batch, longest-first batch queue, scores exchanged through
-// rotating L2-resident buffers with one counter barrier per step, cp.async ring
-// synchronised by mbarriers (deeper here -- 6 stages of 22 KB -- since a stage holds
-// only ~0.3 us of math), fused log-space conversion, fp32 score history.
+// NJT = ceil(S / TN) CTAs per batch, longest-first batch queue, scores exchanged through
+// rotating L2-resident buffers with one counter barrier per step, fused log-space conversion,
+// fp32 score history.
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -56,11 +62,21 @@ struct Streamed16x40 {                // lanes 4 x 8
     static constexpr int kMaxLDP = 1 << 30;
 };
 
+// Resident shape: every warp runs a PRIVATE cp.async pipeline over its own eighth of the source states
+// (double-buffered stages of kWarpSources sources, rows kWarpStride floats apart: 8 rows -> 8 distinct
+// bank groups), synchronised with cp.async.wait_group + __syncwarp only -- no barrier couples the warps
+// inside a step.  A lane copies 16-byte column lane % 8 of rows lane / 8 + 4 q: every copy instruction
+// covers four full 128-byte lines.
+constexpr int kWarpSources = 32, kWarpStride = 36, kWarpStages = 2;
 template <typename Shape>
 constexpr int stage_floats() { return (Shape::TM + (Shape::kResident ? 0 : Shape::TN)) * (Shape::KS + 4); }
 template <typename Shape>
+constexpr int ring_floats() {
+    return Shape::kResident ? kWarps * kWarpStages * Shape::TM * kWarpStride : Shape::NSTAGE * stage_floats<Shape>();
+}
+template <typename Shape>
 size_t smem_bytes(int ldp) {
-    return sizeof(float) * (Shape::NSTAGE * stage_floats<Shape>() + kTileCells + kWarps * kTileCells +
+    return sizeof(float) * (ring_floats<Shape>() + kTileCells + kWarps * kTileCells +
                             (Shape::kResident ? Shape::TN * (ldp + 4) : 0)) +
            sizeof(int) * 2 * Shape::TM + sizeof(u64) * 2 * Shape::NSTAGE;
 }
@@ -74,6 +90,11 @@ __device__ __forceinline__ float lo(u64 v) { return __uint_as_float((unsigned)v)
 __device__ __forceinline__ float hi(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
 }
 __device__ __forceinline__ int ld_acquire_sys(const int32_t *p) {
     int v;
@@ -163,10 +184,11 @@ __global__ void __launch_bounds__(kThreads, 1) forward_split_kernel(const SplitP
     constexpr int KS = Shape::KS, LDS_ = KS + 4, NSTAGE = Shape::NSTAGE, kSteps = KS / 4;
     constexpr int kStageFloats = stage_floats<Shape>();
     static_assert(TM == LANES_B * M && TN == LANES_J * N && TM * TN == kTileCells, "tile shape");
+    static_assert(!Shape::kResident || (TM == 32 && kWarpStages == 2), "per-warp pipeline: lane / 8 + 4 q covers 32 rows");
     static_assert(kSteps % kWarps == 0 && 960 % KS == 0 && (Shape::kResident || TN % (960 / KS) == 0), "stage shape");
     extern __shared__ __align__(16) float smem[];
     float *ring = smem;
-    float *tile = smem + NSTAGE * kStageFloats;                 // [TM][TN] emission -> new score
+    float *tile = smem + ring_floats<Shape>();                  // [TM][TN] emission -> new score
     float *partial = tile + TM * TN;                            // [warp][TM][TN] per-warp maxima
     float *A_res = partial + kWarps * TM * TN;                  // resident shape: [TN][LDP + 4] transition block
     const int LDA = p.LDP + 4;                                  // rows 4 banks apart, like the ring's
@@ -182,7 +204,9 @@ __global__ void __launch_bounds__(kThreads, 1) forward_split_kernel(const SplitP
         mbar_fence_init();
     }
     __syncthreads();
-    unsigned stage_counter = 0;      // stages consumed so far (slot = counter % NSTAGE, full parity = counter / NSTAGE & 1)
+    // ring position of the next stage to consume, kept as wrap-around counters (no modulo in the
+    // stage loop): its slot, and the parity of the full-barrier phase that stage completes
+    unsigned slot = 0, full_parity = 0;
     unsigned empty_parity = 0;       // bit k: parity of the next phase of empty_bar[k] to wait for
     __shared__ int ready_shared;
     int ready = p.frames_ready ? 0 : 0x7fffffff;
@@ -293,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_split_kernel(const SplitP
                 }
             }
             for (int s = 0; s < ahead; ++s)
-                load_stage_A<Shape>(ring + ((stage_counter + s) % NSTAGE) * kStageFloats + ld_smem, ld_A + s * KS, ld_stride10);
+                load_stage_A<Shape>(ring + ((slot + s) % NSTAGE) * kStageFloats + ld_smem, ld_A + s * KS, ld_stride10);
         };
         if (batch_frames > 1) prefetch_step(1);
 
@@ -306,67 +330,126 @@ __global__ void __launch_bounds__(kThreads, 1) forward_split_kernel(const SplitP
             buf = buf_new;
             const float *ld_P = P_cur + (row0 + ld_r0) * LDP + ld_c4 * 4;
 
-            // the score rows of the stages issued ahead (their transition rows went out before the wait)
-            for (int s = 0; s < ahead; ++s) {
-                const unsigned slot = (stage_counter + s) % NSTAGE;
-                load_stage_P<Shape>(ring + slot * kStageFloats + ld_smem, ld_P + s * KS, ld_stride10, ld_r0,
-                                    KS == kStageSources || s * KS + ld_c4 * 4 < LDP);
-                cp_async_arrive(full_bar + slot);
-            }
-
             float cur[M][N];
 #pragma unroll
             for (int i = 0; i < M; ++i)
 #pragma unroll
                 for (int c = 0; c < N; ++c) cur[i][c] = -INFINITY;
 
-            for (int s = 0; s < nstages; ++s, ++stage_counter) {
-                const unsigned slot = stage_counter % NSTAGE;
-                mbar_wait(full_bar + slot, (stage_counter / NSTAGE) & 1);      // everyone's copies have landed
-                if (s == 0) { PROF_MARK(0) }
-                // refill the slot the previous stage used with stage s + NSTAGE - 1
-                if (s + NSTAGE - 1 < nstages) {
-                    const unsigned rslot = (stage_counter + NSTAGE - 1) % NSTAGE;
-                    if (s > 0) {    // (s == 0: its last readers belong to the previous step, behind CTA barriers)
-                        mbar_wait(empty_bar + rslot, (empty_parity >> rslot) & 1u);
-                        empty_parity ^= 1u << rslot;
+            if constexpr (Shape::kResident) {
+                // ---- per-warp private pipelines over the warp's eighth of the sources ----
+                constexpr int KW = kWarpSources, WLD = kWarpStride, WST = kWarpStages;
+                const int L = LDP / kWarps;                       // multiple of 12: LDP is a multiple of 96
+                const int wstages = (L + KW - 1) / KW;            // (the last one may be partial)
+                float *wring = ring + warp * (WST * TM * WLD);
+                const int ld_chunk = (lane % 8) * 4, ld_row = lane / 8;
+                const float *gP = P_cur + (row0 + ld_row) * LDP + warp * L + ld_chunk;
+                float *sP = wring + ld_row * WLD + ld_chunk;
+                auto issue = [&](int st) {
+                    if (st < wstages && st * KW + ld_chunk < L) {
+                        float *dst = sP + (st & 1) * (TM * WLD);
+                        const float *src = gP + st * KW;
+#pragma unroll
+                        for (int q = 0; q < TM / 4; ++q) cp_async16(dst + q * 4 * WLD, src + (int64_t)q * 4 * LDP);
                     }
-                    float *dst = ring + rslot * kStageFloats + ld_smem;
-                    load_stage_A<Shape>(dst, ld_A + (s + NSTAGE - 1) * KS, ld_stride10);
-                    load_stage_P<Shape>(dst, ld_P + (s + NSTAGE - 1) * KS, ld_stride10, ld_r0,
-                                        KS == kStageSources || (s + NSTAGE - 1) * KS + ld_c4 * 4 < LDP);
-                    cp_async_arrive(full_bar + rslot);
-                }
-                const float *Ps = ring + slot * kStageFloats + lane_b * LDS_;
-                const float *As = Shape::kResident ? A_res + lane_j * LDA + s * KS
-                                                   : ring + slot * kStageFloats + (TM + lane_j) * LDS_;
-                const int lda = Shape::kResident ? LDA : LDS_;
+                    cp_async_commit();                            // (empty groups keep the count uniform)
+                };
+                issue(0);
+                const float *Aw = A_res + lane_j * LDA + warp * L;
+                for (int st = 0; st < wstages; ++st) {
+                    cp_async_wait<0>();                           // this lane's copies of stage st have landed ...
+                    __syncwarp();                                 // ... and so have the other lanes'
+                    if (st == 0) { PROF_MARK(0) }
+                    issue(st + 1);             // into the buffer read one iteration ago (every lane is past it)
+                    const float *Ps = wring + (st & 1) * (TM * WLD) + lane_b * WLD;
+                    const float *As = Aw + st * KW;
+                    const int kmax = min(KW, L - st * KW);
+                    // full stages run without a branch between k-steps, so the operand loads of the next
+                    // k-step are scheduled under the math of the current one; only a partial last stage
+                    // pays for the (warp-uniform) bound check
+                    auto k_steps = [&](auto partial_stage) {
 #pragma unroll
-                for (int kk = 0; kk < kSteps / kWarps; ++kk) {
-                    const int k = (warp + kk * kWarps) * 4;          // this warp's share of the stage's sources
-                    // stages wider than the 96-state row padding: the second half of the last one may lie past
-                    // the end of the row (CTA-uniform condition; k >= 96 exactly for the upper half of kk)
-                    if (KS > kStageSources && kk >= kSteps / kWarps / 2 && s == nstages - 1 && LDP % KS != 0) continue;
-                    ulonglong2 pv[M], av[N];
+                        for (int k = 0; k < KW; k += 4) {
+                            if constexpr (decltype(partial_stage)::value) {
+                                if (k >= kmax) break;
+                            }
+                            ulonglong2 pv[M], av[N];
 #pragma unroll
-                    for (int i = 0; i < M; ++i)
-                        pv[i] = *reinterpret_cast<const ulonglong2 *>(Ps + i * LANES_B * LDS_ + k);
+                            for (int i = 0; i < M; ++i)
+                                pv[i] = *reinterpret_cast<const ulonglong2 *>(Ps + i * LANES_B * WLD + k);
 #pragma unroll
-                    for (int c = 0; c < N; ++c)
-                        av[c] = *reinterpret_cast<const ulonglong2 *>(As + c * LANES_J * lda + k);
+                            for (int c = 0; c < N; ++c)
+                                av[c] = *reinterpret_cast<const ulonglong2 *>(As + c * LANES_J * LDA + k);
 #pragma unroll
-                    for (int i = 0; i < M; ++i)
+                            for (int i = 0; i < M; ++i)
 #pragma unroll
-                        for (int c = 0; c < N; ++c) {
-                            const u64 v0 = add2(pv[i].x, av[c].x);
-                            const u64 v1 = add2(pv[i].y, av[c].y);
-                            cur[i][c] = fmaxf(fmaxf(fmaxf(fmaxf(cur[i][c], lo(v0)), hi(v0)), lo(v1)), hi(v1));
+                                for (int c = 0; c < N; ++c) {
+                                    const u64 v0 = add2(pv[i].x, av[c].x);
+                                    const u64 v1 = add2(pv[i].y, av[c].y);
+                                    cur[i][c] = fmaxf(fmaxf(fmaxf(fmaxf(cur[i][c], lo(v0)), hi(v0)), lo(v1)), hi(v1));
+                                }
                         }
+                    };
+                    if (kmax == KW) k_steps(std::false_type{});
+                    else k_steps(std::true_type{});
                 }
-                // signalled only when a refill (during the next stage) is going to wait for it
-                if (s + NSTAGE < nstages) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(empty_bar + slot);
+                cp_async_wait<0>();            // the emission tile's copies as well
+            } else {
+                // the score rows of the stages issued ahead (their transition rows went out before the wait)
+                for (int s = 0; s < ahead; ++s) {
+                    const unsigned aslot = (slot + s) % NSTAGE;
+                    load_stage_P<Shape>(ring + aslot * kStageFloats + ld_smem, ld_P + s * KS, ld_stride10, ld_r0,
+                                        KS == kStageSources || s * KS + ld_c4 * 4 < LDP);
+                    cp_async_arrive(full_bar + aslot);
+                }
+                for (int s = 0; s < nstages; ++s) {
+                    mbar_wait(full_bar + slot, full_parity);                       // everyone's copies have landed
+                    if (s == 0) { PROF_MARK(0) }
+                    // refill the slot the previous stage used with stage s + NSTAGE - 1
+                    if (s + NSTAGE - 1 < nstages) {
+                        const unsigned rslot = slot == 0 ? NSTAGE - 1 : slot - 1;
+                        if (s > 0) {    // (s == 0: its last readers belong to the previous step, behind CTA barriers)
+                            mbar_wait(empty_bar + rslot, (empty_parity >> rslot) & 1u);
+                            empty_parity ^= 1u << rslot;
+                        }
+                        float *dst = ring + rslot * kStageFloats + ld_smem;
+                        load_stage_A<Shape>(dst, ld_A + (s + NSTAGE - 1) * KS, ld_stride10);
+                        load_stage_P<Shape>(dst, ld_P + (s + NSTAGE - 1) * KS, ld_stride10, ld_r0,
+                                            KS == kStageSources || (s + NSTAGE - 1) * KS + ld_c4 * 4 < LDP);
+                        cp_async_arrive(full_bar + rslot);
+                    }
+                    const float *Ps = ring + slot * kStageFloats + lane_b * LDS_;
+                    const float *As = Shape::kResident ? A_res + lane_j * LDA + s * KS
+                                                       : ring + slot * kStageFloats + (TM + lane_j) * LDS_;
+                    const int lda = Shape::kResident ? LDA : LDS_;
+    #pragma unroll
+                    for (int kk = 0; kk < kSteps / kWarps; ++kk) {
+                        const int k = (warp + kk * kWarps) * 4;          // this warp's share of the stage's sources
+                        // stages wider than the 96-state row padding: the second half of the last one may lie past
+                        // the end of the row (CTA-uniform condition; k >= 96 exactly for the upper half of kk)
+                        if (KS > kStageSources && kk >= kSteps / kWarps / 2 && s == nstages - 1 && LDP % KS != 0) continue;
+                        ulonglong2 pv[M], av[N];
+    #pragma unroll
+                        for (int i = 0; i < M; ++i)
+                            pv[i] = *reinterpret_cast<const ulonglong2 *>(Ps + i * LANES_B * LDS_ + k);
+    #pragma unroll
+                        for (int c = 0; c < N; ++c)
+                            av[c] = *reinterpret_cast<const ulonglong2 *>(As + c * LANES_J * lda + k);
+    #pragma unroll
+                        for (int i = 0; i < M; ++i)
+    #pragma unroll
+                            for (int c = 0; c < N; ++c) {
+                                const u64 v0 = add2(pv[i].x, av[c].x);
+                                const u64 v1 = add2(pv[i].y, av[c].y);
+                                cur[i][c] = fmaxf(fmaxf(fmaxf(fmaxf(cur[i][c], lo(v0)), hi(v0)), lo(v1)), hi(v1));
+                            }
+                    }
+                    // signalled only when a refill (during the next stage) is going to wait for it
+                    if (s + NSTAGE < nstages) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(empty_bar + slot);
+                    }
+                    if (++slot == NSTAGE) { slot = 0; full_parity ^= 1u; }
                 }
             }
             if (!obs_vec) __syncthreads();              // plain-store emission tile: make it visible
@@ -468,7 +551,7 @@ double split_estimate_seconds(const int32_t *frames_sorted, int64_t B, int64_t S
     const bool resident = resident_shape(S, sm_count);
     const int tm = resident ? Resident32x20::TM : Streamed16x40::TM;
     const int tn = resident ? Resident32x20::TN : Streamed16x40::TN;
-    const double step_seconds = resident ? 13.3e-6 : 14.1e-6;      // per 32-row / 16-row batch
+    const double step_seconds = resident ? 12.7e-6 : 14.1e-6;      // per 32-row / 16-row batch
     const int njt = (int)((S + tn - 1) / tn);
     const int batches = (int)((B + tm - 1) / tm);
     const int groups = std::max(1, std::min(sm_count / std::max(njt, 1), batches));
