@@ -459,14 +459,26 @@ int decode_items_on_device(const float *observation, const int32_t *batch_frames
     const bool can_tile = padded_dests(S) / kTileDests <= info.sm_count && !(flags & TORBI_B200_FORCE_GENERIC);
     const bool stream_in = pinned && can_tile && T >= 64 && row_bytes < (size_t(1) << 31) &&
                            (size_t)count * row_bytes >= (size_t(64) << 20);
-    const int chunks = stream_in ? (int)std::min<int64_t>(16, std::max<int64_t>(2, T / 64)) : 1;
+    const int chunks = stream_in ? (int)std::min<int64_t>(kMaxChunks, std::max<int64_t>(2, T / 64)) : 1;
+    // Chunk boundaries along T.  The forward kernel cannot start before the first chunk has landed, so
+    // with 16 chunks the first ones ramp up geometrically (T/128, T/64, T/32, T/16) and the rest follows
+    // in equal parts.  (Measured at config 2, profiles/r01_e2e_copy_experiments.txt: worth 0.3 %; the
+    // same ramp mirrored at the end, or the halves of every chunk on two copy streams, are SLOWER.)
+    std::vector<int64_t> bound(chunks + 1);
+    for (int c = 0; c <= chunks; ++c) bound[c] = T * c / chunks;
+    if (chunks == kMaxChunks && T >= 1024) {
+        const int ramp = 4;
+        for (int c = 1; c <= ramp; ++c) bound[c] = T >> (8 - c);
+        for (int c = ramp + 1; c < chunks; ++c)
+            bound[c] = bound[ramp] + (T - bound[ramp]) * (c - ramp) / (chunks - ramp);
+    }
     if (stream_in) {
         e = cudaMemsetAsync(d_ready, 0, sizeof(int32_t), arena->copy_stream);
         if (e == cudaSuccess) e = cudaEventRecord(arena->reset_event, arena->copy_stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, arena->reset_event, 0);
     }
     for (int c = 0; c < chunks && e == cudaSuccess; ++c) {
-        const int64_t t0 = T * c / chunks, t1 = T * (c + 1) / chunks;
+        const int64_t t0 = bound[c], t1 = bound[c + 1];
         // items that are consecutive in the caller's batch travel in one copy
         for (int64_t i = 0; i < count && e == cudaSuccess;) {
             int64_t run = 1;
