@@ -357,7 +357,7 @@ int torbi_b200_last_timing(float *forward_ms, float *backtrace_ms) {
 // ---------------------------------------------------------------------------
 namespace {
 
-constexpr int kMaxChunks = 16;
+constexpr int kMaxChunks = 64;
 
 struct Arena {
     void *base = nullptr;
@@ -459,18 +459,20 @@ int decode_items_on_device(const float *observation, const int32_t *batch_frames
     const bool can_tile = padded_dests(S) / kTileDests <= info.sm_count && !(flags & TORBI_B200_FORCE_GENERIC);
     const bool stream_in = pinned && can_tile && T >= 64 && row_bytes < (size_t(1) << 31) &&
                            (size_t)count * row_bytes >= (size_t(64) << 20);
-    const int chunks = stream_in ? (int)std::min<int64_t>(kMaxChunks, std::max<int64_t>(2, T / 64)) : 1;
-    // Chunk boundaries along T.  The forward kernel cannot start before the first chunk has landed, so
-    // with 16 chunks the first ones ramp up geometrically (T/128, T/64, T/32, T/16) and the rest follows
-    // in equal parts.  (Measured at config 2, profiles/r01_e2e_copy_experiments.txt: worth 0.3 %; the
-    // same ramp mirrored at the end, or the halves of every chunk on two copy streams, are SLOWER.)
+    const int chunks = stream_in ? (int)std::min<int64_t>(kMaxChunks, std::max<int64_t>(2, T / 16)) : 1;
+    // Chunk boundaries along T.  The forward kernel trails the copy by one chunk (step t needs the whole
+    // chunk holding frame t), and at config 2 the copy is only ~1.3x faster than the kernel consumes
+    // frames, so what is exposed is roughly the FIRST chunk's copy time: many small chunks (64: 1.7 ms
+    // each at config 2 instead of 6.6 ms with 16), the first two halved again.  Chunks must not grow
+    // faster than that 1.3x either: a geometric ramp T/128, T/64, ... stalls the kernel for 7 ms at the
+    // first big chunk (profiles/r01_e2e_copy_experiments.txt).
     std::vector<int64_t> bound(chunks + 1);
     for (int c = 0; c <= chunks; ++c) bound[c] = T * c / chunks;
-    if (chunks == kMaxChunks && T >= 1024) {
-        const int ramp = 4;
-        for (int c = 1; c <= ramp; ++c) bound[c] = T >> (8 - c);
-        for (int c = ramp + 1; c < chunks; ++c)
-            bound[c] = bound[ramp] + (T - bound[ramp]) * (c - ramp) / (chunks - ramp);
+    if (chunks == kMaxChunks && T >= 4 * kMaxChunks) {
+        bound[1] = T / (4 * chunks);
+        bound[2] = T / (2 * chunks);
+        bound[3] = T / chunks;
+        for (int c = 4; c < chunks; ++c) bound[c] = bound[3] + (T - bound[3]) * (c - 3) / (chunks - 3);
     }
     if (stream_in) {
         e = cudaMemsetAsync(d_ready, 0, sizeof(int32_t), arena->copy_stream);
