@@ -313,3 +313,33 @@ def test_native_file_reader_and_writer(tmp_path):
         native.save_int32([torch.zeros(3)], [tmp_path / 'bad.pt'])
     with pytest.raises(OSError):
         native.save_int32([outputs[0]], [tmp_path / 'no_such_dir' / 'x.pt'])
+
+
+def test_native_reader_rejects_damaged_files(tmp_path):
+    """Truncated, corrupted or empty containers are reported per file, never read out of bounds."""
+    from torbi_b200.data import native
+    good = tmp_path / 'good.pt'
+    torch.save(torch.arange(24, dtype=torch.float32).reshape(4, 6), good)
+    raw = good.read_bytes()
+    cases_ = {
+        'empty.pt': b'',
+        'short.pt': raw[:10],
+        'truncated.pt': raw[:len(raw) // 2],
+        'no_directory.pt': raw[:-30],
+        'garbage.pt': bytes(range(256)) * 8,
+    }
+    # a central directory that points past the end of the file
+    bad = bytearray(raw)
+    eocd = raw.rfind(b'PK\x05\x06')
+    bad[eocd + 16:eocd + 20] = (len(raw) + 1000).to_bytes(4, 'little')
+    cases_['bad_offset.pt'] = bytes(bad)
+    # a pickle that is not a tensor record
+    flipped = bytearray(raw)
+    at = raw.find(b'_rebuild_tensor_v2')
+    flipped[at:at + 8] = b'_REBUILD'
+    cases_['other_pickle.pt'] = bytes(flipped)
+    for name, data in cases_.items():
+        (tmp_path / name).write_bytes(data)
+    infos = native.inspect([tmp_path / name for name in cases_] + [good])
+    assert all(info.status != 0 for info in infos[:-1]), [info.status for info in infos]
+    assert infos[-1].status == 0

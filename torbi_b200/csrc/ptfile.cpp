@@ -47,6 +47,14 @@ bool read_at(int fd, void *buffer, size_t bytes, uint64_t offset) {
 uint16_t u16(const unsigned char *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
 uint32_t u32(const unsigned char *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 
+struct FileDescriptor {                  // closes on every path, exceptions included
+    int fd;
+    explicit FileDescriptor(int fd_) : fd(fd_) {}
+    ~FileDescriptor() { if (fd >= 0) close(fd); }
+    FileDescriptor(const FileDescriptor &) = delete;
+    FileDescriptor &operator=(const FileDescriptor &) = delete;
+};
+
 struct Entry {
     std::string name;
     uint64_t local_offset = 0, size = 0;
@@ -146,7 +154,7 @@ int parse_tensor_pickle(const std::vector<unsigned char> &pkl, TensorRecord *out
         return true;
     };
     auto memoize = [&](size_t index) {
-        if (stack.empty()) return false;
+        if (stack.empty() || index > 4096) return false;           // (a tensor record memoizes a dozen values)
         if (memo.size() <= index) memo.resize(index + 1);
         memo[index] = stack.back();
         return true;
@@ -296,9 +304,24 @@ bool ends_with(const std::string &text, const std::string &suffix) {
     return text.size() >= suffix.size() && text.compare(text.size() - suffix.size(), suffix.size(), suffix) == 0;
 }
 
+int inspect_one_unchecked(const char *path, torbi_b200_pt_info *info);
+
+// no C++ exception may cross the C ABI: anything unexpected (allocation failure on a hostile size
+// field, ...) makes the file "unsupported" and the caller falls back to torch.load
 int inspect_one(const char *path, torbi_b200_pt_info *info) {
+    try {
+        return inspect_one_unchecked(path, info);
+    } catch (...) {
+        std::memset(info, 0, sizeof(*info));
+        info->status = TORBI_B200_PT_UNSUPPORTED;
+        return TORBI_B200_PT_UNSUPPORTED;
+    }
+}
+
+int inspect_one_unchecked(const char *path, torbi_b200_pt_info *info) {
     std::memset(info, 0, sizeof(*info));
-    const int fd = open(path, O_RDONLY | O_CLOEXEC);
+    const FileDescriptor file(open(path, O_RDONLY | O_CLOEXEC));
+    const int fd = file.fd;
     if (fd < 0) {
         info->status = TORBI_B200_PT_IO_ERROR;
         return TORBI_B200_PT_IO_ERROR;
@@ -345,7 +368,11 @@ int inspect_one(const char *path, torbi_b200_pt_info *info) {
             // contiguous (row-major) views only
             int64_t numel = 1, expect = 1;
             for (int d = (int)tensor.shape.size() - 1; d >= 0; --d) {
-                if (tensor.shape[d] < 0) rc = TORBI_B200_PT_UNSUPPORTED;
+                // (bounded so that the products below cannot overflow)
+                if (tensor.shape[d] < 0 || tensor.shape[d] > (int64_t(1) << 40) || numel > (int64_t(1) << 20) * (int64_t(1) << 20) / std::max<int64_t>(tensor.shape[d], 1)) {
+                    rc = TORBI_B200_PT_UNSUPPORTED;
+                    break;
+                }
                 if (tensor.shape[d] > 1 && tensor.stride[d] != expect) rc = TORBI_B200_PT_UNSUPPORTED;
                 expect *= std::max<int64_t>(tensor.shape[d], 1);
                 numel *= tensor.shape[d];
@@ -353,7 +380,8 @@ int inspect_one(const char *path, torbi_b200_pt_info *info) {
             uint64_t at = 0;
             if (rc == TORBI_B200_PT_OK) rc = entry_data_offset(fd, *storage, &at);
             if (rc == TORBI_B200_PT_OK &&
-                ((uint64_t)(tensor.offset + numel) * itemsize > storage->size || at + storage->size > (uint64_t)st.st_size))
+                (tensor.offset > (int64_t(1) << 40) || (uint64_t)(tensor.offset + numel) * itemsize > storage->size ||
+                 at + storage->size > (uint64_t)st.st_size))
                 rc = TORBI_B200_PT_UNSUPPORTED;
             if (rc == TORBI_B200_PT_OK) {
                 info->data_offset = (int64_t)at + tensor.offset * itemsize;
@@ -364,7 +392,6 @@ int inspect_one(const char *path, torbi_b200_pt_info *info) {
             }
         }
     }
-    close(fd);
     info->status = rc;
     return rc;
 }
@@ -474,7 +501,17 @@ void append_record(std::string *file, std::vector<Record> *records, const std::s
     records->push_back(std::move(record));
 }
 
+int write_one_i32_unchecked(const char *path, const int32_t *data, const int64_t *shape, int ndim);
+
 int write_one_i32(const char *path, const int32_t *data, const int64_t *shape, int ndim) {
+    try {
+        return write_one_i32_unchecked(path, data, shape, ndim);
+    } catch (...) {
+        return TORBI_B200_PT_IO_ERROR;
+    }
+}
+
+int write_one_i32_unchecked(const char *path, const int32_t *data, const int64_t *shape, int ndim) {
     int64_t numel = 1;
     for (int d = 0; d < ndim; ++d) numel *= shape[d];
     if (ndim < 0 || ndim > 4 || numel < 0 || (uint64_t)numel * 4 > 0x7fffffffu) return TORBI_B200_PT_UNSUPPORTED;
@@ -521,16 +558,21 @@ extern "C" {
 
 int torbi_b200_pt_inspect(const char *const *paths, int64_t n, torbi_b200_pt_info *info, int threads) {
     if (!paths || !info || n < 0) return TORBI_B200_ERR_INVALID_ARGUMENT;
-    std::atomic<int> failures{0};
-    parallel_for(n, threads, [&](int64_t i) {
-        if (inspect_one(paths[i], &info[i]) != TORBI_B200_PT_OK) failures.fetch_add(1);
-    });
-    return failures.load();
+    try {
+        std::atomic<int> failures{0};
+        parallel_for(n, threads, [&](int64_t i) {
+            if (inspect_one(paths[i], &info[i]) != TORBI_B200_PT_OK) failures.fetch_add(1);
+        });
+        return failures.load();
+    } catch (...) {                      // (thread creation failure)
+        return TORBI_B200_ERR_OUT_OF_MEMORY;
+    }
 }
 
 int torbi_b200_pt_read(const char *const *paths, const torbi_b200_pt_info *info, int64_t n,
                        void *const *destinations, const int64_t *capacities, int threads) {
     if (!paths || !info || !destinations || !capacities || n < 0) return TORBI_B200_ERR_INVALID_ARGUMENT;
+    try {
     // split large payloads so a batch of few big files still uses every thread
     struct Piece { int64_t file; uint64_t begin, end; };
     std::vector<Piece> pieces;
@@ -560,16 +602,23 @@ int torbi_b200_pt_read(const char *const *paths, const torbi_b200_pt_info *info,
         if (zero_from < piece.end) std::memset(dst + zero_from, 0, piece.end - zero_from);
     });
     return failures.load();
+    } catch (...) {
+        return TORBI_B200_ERR_OUT_OF_MEMORY;
+    }
 }
 
 int torbi_b200_pt_write_i32(const char *const *paths, const int32_t *const *data, const int64_t *shapes,
                             const int32_t *ndims, int64_t n, int threads) {
     if (!paths || !data || !shapes || !ndims || n < 0) return TORBI_B200_ERR_INVALID_ARGUMENT;
-    std::atomic<int> failures{0};
-    parallel_for(n, threads, [&](int64_t i) {
-        if (write_one_i32(paths[i], data[i], shapes + 4 * i, ndims[i]) != TORBI_B200_PT_OK) failures.fetch_add(1);
-    });
-    return failures.load();
+    try {
+        std::atomic<int> failures{0};
+        parallel_for(n, threads, [&](int64_t i) {
+            if (write_one_i32(paths[i], data[i], shapes + 4 * i, ndims[i]) != TORBI_B200_PT_OK) failures.fetch_add(1);
+        });
+        return failures.load();
+    } catch (...) {
+        return TORBI_B200_ERR_OUT_OF_MEMORY;
+    }
 }
 
 }  // extern "C"
