@@ -10,6 +10,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <new>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -90,6 +91,20 @@ int device_info(int device, DeviceInfo *out) {
                     "device %d has compute capability %d.x; libtorbi_b200 carries sm_100a code only",
                     device, out->cc_major);
     return TORBI_B200_OK;
+}
+
+// No C++ exception may cross the C ABI (host allocations for a huge batch, thread creation).
+template <typename Fn>
+int guarded(Fn fn) {
+    try {
+        return fn();
+    } catch (const std::bad_alloc &) {
+        return fail(TORBI_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
+    } catch (const std::exception &error) {
+        return fail(TORBI_B200_ERR_CUDA, "internal error: %s", error.what());
+    } catch (...) {
+        return fail(TORBI_B200_ERR_CUDA, "internal error");
+    }
 }
 
 int validate_shape(int64_t B, int64_t T, int64_t S) {
@@ -313,14 +328,17 @@ int torbi_b200_decode(const float *observation, const int32_t *batch_frames,
                       const float *transition, const float *initial, int64_t B, int64_t T,
                       int64_t S, uint32_t flags, int32_t *indices, float *posterior,
                       void *workspace, size_t workspace_bytes, void *stream) {
-    return decode_device(observation, batch_frames, transition, initial, B, T, S, flags, indices,
-                         posterior, workspace, workspace_bytes, stream, nullptr, nullptr);
+    return guarded([&] {
+        return decode_device(observation, batch_frames, transition, initial, B, T, S, flags, indices,
+                             posterior, workspace, workspace_bytes, stream, nullptr, nullptr);
+    });
 }
 
 const char *torbi_b200_plan(const int32_t *batch_frames, int64_t B, int64_t T, int64_t S,
                             uint32_t flags, int sm_count) {
     g_error[0] = 0;
     if (validate_shape(B, T, S) != TORBI_B200_OK || !batch_frames || sm_count < 1) return nullptr;
+    try {
     std::vector<int32_t> order(pad_batch(B), -1);
     std::iota(order.begin(), order.begin() + B, 0);
     std::stable_sort(order.begin(), order.begin() + B,
@@ -334,6 +352,10 @@ const char *torbi_b200_plan(const int32_t *batch_frames, int64_t B, int64_t T, i
     Choice choice = kGeneric;
     if (choose_kernel(a, batch_frames, order, flags, &choice) != TORBI_B200_OK) return nullptr;
     return kernel_name(a, choice, flags);
+    } catch (...) {
+        fail(TORBI_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
+        return nullptr;
+    }
 }
 
 int torbi_b200_last_timing(float *forward_ms, float *backtrace_ms) {
@@ -548,10 +570,12 @@ int torbi_b200_decode_host(const float *observation, const int32_t *batch_frames
     g_error[0] = 0;
     int rc = validate_host_args(observation, batch_frames, transition, initial, B, T, S, indices);
     if (rc) return rc;
-    std::vector<int32_t> items(B);
-    std::iota(items.begin(), items.end(), 0);
-    return decode_items_on_device(observation, batch_frames, transition, initial, items.data(), B,
-                                  T, S, flags, indices, posterior, device);
+    return guarded([&] {
+        std::vector<int32_t> items(B);
+        std::iota(items.begin(), items.end(), 0);
+        return decode_items_on_device(observation, batch_frames, transition, initial, items.data(), B,
+                                      T, S, flags, indices, posterior, device);
+    });
 }
 
 int torbi_b200_decode_host_multi(const float *observation, const int32_t *batch_frames,
@@ -563,6 +587,7 @@ int torbi_b200_decode_host_multi(const float *observation, const int32_t *batch_
     if (rc) return rc;
     if (!devices || n_devices < 1)
         return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "need at least one device");
+    return guarded([&] {
     const int n = (int)std::min<int64_t>(n_devices, B);
 
     // longest-processing-time-first: cost of an item is proportional to its
@@ -585,9 +610,11 @@ int torbi_b200_decode_host_multi(const float *observation, const int32_t *batch_
     std::vector<std::thread> workers;
     for (int k = 0; k < n; ++k) {
         workers.emplace_back([&, k] {
-            status[k] = decode_items_on_device(observation, batch_frames, transition, initial,
-                                               shard[k].data(), (int64_t)shard[k].size(), T, S,
-                                               flags, indices, posterior, devices[k]);
+            status[k] = guarded([&] {
+                return decode_items_on_device(observation, batch_frames, transition, initial,
+                                              shard[k].data(), (int64_t)shard[k].size(), T, S,
+                                              flags, indices, posterior, devices[k]);
+            });
             if (status[k]) message[k] = torbi_b200_last_error();
         });
     }
@@ -595,6 +622,7 @@ int torbi_b200_decode_host_multi(const float *observation, const int32_t *batch_
     for (int k = 0; k < n; ++k)
         if (status[k]) return fail(status[k], "device %d: %s", devices[k], message[k].c_str());
     return TORBI_B200_OK;
+    });
 }
 
 int torbi_b200_selftest_conversion(uint64_t *mismatches) {
