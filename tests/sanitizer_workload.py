@@ -1,5 +1,6 @@
 """Small decodes through every kernel for compute-sanitizer (memcheck / racecheck /
-initcheck / synccheck):  compute-sanitizer --tool memcheck python tools/sanitize.py"""
+initcheck / synccheck):  compute-sanitizer --tool memcheck python tests/sanitizer_workload.py
+(test infrastructure: the only reason it lives under tests/ is that it checks against the oracle)"""
 import pathlib
 import sys
 

@@ -15,6 +15,6 @@ for line in open('gpurun_out/batch_sweep.jsonl'):
     print(d['config']['batch_per_gpu'], round(d['value']), d['roofline']['kernel'], round(d['roofline']['frac'], 3))
 PY
 for tool in memcheck racecheck synccheck initcheck; do
-  timeout 280 compute-sanitizer --tool $tool python tools/sanitize.py > gpurun_out/sanitizer_$tool.log 2>&1
+  timeout 280 compute-sanitizer --tool $tool python tests/sanitizer_workload.py > gpurun_out/sanitizer_$tool.log 2>&1
   echo "$tool rc=$? ok=$(grep -c '^ok' gpurun_out/sanitizer_$tool.log) $(grep SUMMARY gpurun_out/sanitizer_$tool.log)"
 done
