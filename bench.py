@@ -7,9 +7,12 @@ batch 512, 2000 frames, triangular transition (BASELINE.json config 2).
 A "step" is one pass of the hot path over one batch of synthetic input.  For
 N > 1 the driver launches one process per GPU (torchrun); every rank decodes its
 own batch of 512 sequences (weak scaling: the path shards over independent
-sequences, no data-path collective) and rank 0 prints ONE JSON line.
-`--scaling strong` (not what the driver runs) instead splits ONE batch of 512 over the N
-ranks -- 512 / N sequences per GPU, decoded by the split-K small-tile kernel.
+sequences, no data-path collective) and rank 0 prints ONE JSON line.  The same
+invocation also measures STRONG scaling -- one global batch of 512 sequences,
+512 / N per GPU -- and reports it under "strong"; at N = 1 the line carries
+BASELINE configs 1, 3 and 5 under "configs" (device-timed, with clocks).
+Every rank binds its host threads to the NUMA node of its GPU before it
+allocates pinned memory ("host_binding" in config).
 
   value      whole-job timesteps/s with inputs resident in HBM, CUDA events, max over ranks
   e2e        the same through the C ABI host entry (torbi_b200_decode_host): pinned host
@@ -57,9 +60,13 @@ def parse_args():
     parser.add_argument('--cpu-seconds', type=float, default=None,
                         help='CPU work per reference step / cpu_baseline sample (default: sized automatically)')
     parser.add_argument('--no-cpu-baseline', action='store_true')
-    parser.add_argument('--kernel', default='auto', choices=['auto', 'generic', 'tiled', 'wide', 'split'])
+    parser.add_argument('--kernel', default='auto', choices=['auto', 'generic', 'tiled', 'wide', 'split', 'cluster'])
+    parser.add_argument('--no-strong', action='store_true', help='skip the strong-scaling leg (N > 1)')
+    parser.add_argument('--no-configs', action='store_true', help='skip BASELINE configs 1 / 3 / 5 (N = 1)')
+    parser.add_argument('--skip-config3', action='store_true')
+    parser.add_argument('--skip-config5', action='store_true')
+    parser.add_argument('--config5-frames', type=int, default=1_000_000)
     parser.add_argument('--tile-rows', type=int, default=0, choices=[0, 16, 32, 64])
-    parser.add_argument('--ws', action='store_true', help='warp-specialised tiled kernel')
     parser.add_argument('--split-streamed', action='store_true', help='split kernel: streamed 16 x 40 tiles')
     parser.add_argument('--backpointers', action='store_true',
                         help="tiled kernel in backpointer mode (uint16 trellis) instead of score history + recomputed backtrace")
@@ -189,9 +196,11 @@ def cpu_sample(args, seconds, seed=1234):
     init = np.full((S,), np.log(1.0 / S + np.finfo(np.float32).tiny), np.float32)
     probe = cases.log_softmax(rng.standard_normal((1, 33, S)))
     run(probe[:, :5], np.array([5], np.int32), A, init)                 # warm the thread pool
-    t0 = time.perf_counter()
-    run(probe, np.array([33], np.int32), A, init)
-    rate = 32 / (time.perf_counter() - t0)                              # recursion steps / s
+    rate = 0.0
+    for _ in range(3):                                                  # (the first passes still ramp up)
+        t0 = time.perf_counter()
+        run(probe, np.array([33], np.int32), A, init)
+        rate = max(rate, 32 / (time.perf_counter() - t0))               # recursion steps / s
     total = int(max(64, min(rate * seconds, 8 * args.frames)))
     B = max(1, min(8, total // args.frames)) if total >= args.frames else 1
     T = max(2, min(args.frames, total // B))
@@ -232,21 +241,166 @@ def bench_reference(args):
 # our arm
 # ---------------------------------------------------------------------------
 
+def bind_to_gpu_numa_node(local, world):
+    """Pin this rank's host threads (and, through first touch, the pinned buffers it allocates from
+    here on) to the CPUs of the NUMA node its GPU hangs off.  With N ranks on one box all inheriting
+    the full CPU mask, the pinned staging buffers otherwise land on whatever node the allocating
+    thread happened to run on and half of the host->device traffic crosses the socket interconnect.
+    Falls back to an even split of the inherited mask when sysfs has no NUMA information."""
+    info = {'method': 'none'}
+    if os.environ.get('TORBI_B200_NO_BIND') == '1' or not hasattr(os, 'sched_setaffinity'):
+        return info
+    allowed = sorted(os.sched_getaffinity(0))
+    try:
+        props = torch.cuda.get_device_properties(local)
+        bus = f'{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0'
+        node = int(pathlib.Path(f'/sys/bus/pci/devices/{bus}/numa_node').read_text())
+        if node >= 0:
+            cpus = set()
+            for part in pathlib.Path(f'/sys/devices/system/node/node{node}/cpulist').read_text().strip().split(','):
+                lo, _, hi = part.partition('-')
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus &= set(allowed)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                return {'method': 'numa', 'numa_node': node, 'cpus': len(cpus), 'pci': bus}
+    except (OSError, ValueError, AttributeError):
+        pass
+    if world > 1 and len(allowed) >= world:
+        share = len(allowed) // world
+        os.sched_setaffinity(0, allowed[local * share:(local + 1) * share])
+        info = {'method': 'even split of the inherited mask', 'cpus': share}
+    return info
+
+
+def synthetic_observations(B, T, S, device, seed, chunk_bytes=2 << 30):
+    g = torch.Generator(device=device).manual_seed(seed)
+    obs = torch.empty((B, T, S), dtype=torch.float32, device=device)
+    rows = max(1, int(chunk_bytes // (T * S * 4)))
+    for start in range(0, B, rows):
+        n = min(rows, B - start)
+        if rows == 1 and T * S * 4 > chunk_bytes:                 # one long sequence: chunk along T
+            step = max(1, int(chunk_bytes // (S * 4)))
+            for t0 in range(0, T, step):
+                x = torch.randn((min(step, T - t0), S), device=device, generator=g)
+                obs[start, t0:t0 + x.shape[0]] = torch.log_softmax(x, dim=-1)
+                del x
+        else:
+            x = torch.randn((n, T, S), device=device, generator=g)
+            obs[start:start + n] = torch.log_softmax(x, dim=-1)
+            del x
+    return obs
+
+
 def make_workload(args, device, seed):
     import cases
     B, T, S = args.batch, args.frames, args.states
-    g = torch.Generator(device=device).manual_seed(seed)
-    obs = torch.empty((B, T, S), dtype=torch.float32, device=device)
-    chunk = max(1, B // 8)
-    for start in range(0, B, chunk):
-        x = torch.randn((min(chunk, B - start), T, S), device=device, generator=g)
-        obs[start:start + x.shape[0]] = torch.log_softmax(x, dim=-1)
-        del x
+    obs = synthetic_observations(B, T, S, device, seed)
     A = torch.from_numpy(cases.log_triangular_transition(S)).to(device)
     init = torch.full((S,), float(np.log(1.0 / S + np.finfo(np.float32).tiny)),
                       dtype=torch.float32, device=device)
     frames = torch.full((B,), T, dtype=torch.int32)
     return obs, frames, A, init
+
+
+def timed_decode(lib, obs, frames, A, init, flags, steps, warmup, barrier, local):
+    """`steps` decodes of one resident batch bracketed by CUDA events (barrier + synchronize on both
+    sides), clocks sampled during the timed region, per-kernel device times from the library."""
+    import ctypes
+    import torbi_b200
+    from torbi_b200 import _ffi
+    fwd_ms, back_ms = [], []
+    indices = None
+    for _ in range(warmup):
+        indices = torbi_b200.decode(obs, frames, A, init, flags=flags)
+    barrier()
+    launches0 = lib.torbi_b200_launch_count()
+    torch.cuda.reset_peak_memory_stats()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        start.record()
+        for _ in range(steps):
+            indices = torbi_b200.decode(obs, frames, A, init, flags=flags)
+            f, b = ctypes.c_float(), ctypes.c_float()
+            _ffi.check(lib.torbi_b200_last_timing(ctypes.byref(f), ctypes.byref(b)))
+            fwd_ms.append(f.value)
+            back_ms.append(b.value)
+        end.record()
+        barrier()
+    return {
+        'elapsed_ms': start.elapsed_time(end), 'fwd_ms': statistics.mean(fwd_ms), 'back_ms': statistics.mean(back_ms),
+        'kernel': lib.torbi_b200_last_kernel().decode(), 'backtrace': lib.torbi_b200_last_backtrace().decode(),
+        'launches': int(lib.torbi_b200_launch_count() - launches0), 'clocks': clocks.summary(),
+        'checksum': int(indices.sum(dtype=torch.int64)), 'indices': indices,
+        'peak_hbm_gb': torch.cuda.max_memory_allocated() / 1e9,
+    }
+
+
+def fp32_peak(sm_count, peaks):
+    return sm_count * 128 * peaks['sm_max_mhz'] * 1e6 / 1e12       # T lane-op/s
+
+
+def other_configs(lib, device, local, peaks, sm_count, barrier, args):
+    """BASELINE configs 1, 3 and 5 on this GPU (N = 1 only), device-timed like the headline: inputs
+    resident in HBM, CUDA events, clocks sampled during the timed region.  Each entry names its kernel,
+    its fraction of the FP32 max-plus issue roofline (2 S^2 lane-ops per timestep) and the peak HBM in use."""
+    import cases
+    from torbi_b200 import _ffi
+    out = {}
+    flags = _ffi.EPS_FLOOR | _ffi.TIME_KERNELS
+
+    def entry(name, obs, frames, A, init, steps, warmup, note):
+        S = obs.shape[2]
+        r = timed_decode(lib, obs, frames, A, init, flags, steps, warmup, barrier, local)
+        timesteps = int(frames.sum())
+        value = timesteps * steps / (r['elapsed_ms'] * 1e-3)
+        out[name] = {
+            'workload': note, 'value': value, 'unit': UNIT, 'ms_per_step': r['elapsed_ms'] / steps, 'steps': steps,
+            'warmup': warmup, 'kernel': r['kernel'], 'backtrace': r['backtrace'], 'forward_ms': r['fwd_ms'],
+            'backtrace_ms': r['back_ms'],
+            'frac_fp32_maxplus': 2.0 * S * S * timesteps / (r['fwd_ms'] * 1e-3) / 1e12 / fp32_peak(sm_count, peaks),
+            'peak_hbm_gb': r['peak_hbm_gb'], 'clocks': r['clocks'], 'checksum': r['checksum']}
+
+    # config 1: 1440 states, batch 1, 2000 frames, default uniform transition / initial
+    S, T = 1440, 2000
+    obs = synthetic_observations(1, T, S, device, 1234)
+    A = torch.full((S, S), float(np.log(1.0 / S)), device=device)
+    init = torch.full((S,), float(np.log(1.0 / S + np.finfo(np.float32).tiny)), device=device)
+    entry('c1', obs, torch.tensor([T], dtype=torch.int32), A, init, 10, 3,
+          'config 1 on the GPU: S=1440, B=1, T=2000, uniform transition / initial (barrier-latency bound, not FP32 bound)')
+    del obs
+
+    # config 3: 1440 states, batch 256, 200..20000 frames (log-uniform), triangular transition
+    if not args.skip_config3:
+        rng = np.random.default_rng(1234)
+        lengths = np.exp(rng.uniform(np.log(200), np.log(20000), size=256)).round().astype(np.int32)
+        lengths[0], lengths[1] = 20000, 200
+        obs = synthetic_observations(256, 20000, S, device, 4321)
+        A = torch.from_numpy(cases.log_triangular_transition(S)).to(device)
+        entry('c3', obs, torch.from_numpy(lengths), A, init, 3, 3,
+              'config 3: S=1440, B=256, 200..20000 frames (log-uniform, seed 1234), triangular transition, dense path; '
+              'bound by the 20000 sequential steps of its longest item')
+        del obs
+    torch.cuda.empty_cache()
+
+    # config 5: 4096 states, batch 1, 10^6 frames, dense transition
+    if not args.skip_config5:
+        S, T = 4096, args.config5_frames
+        obs = synthetic_observations(1, T, S, device, 55)
+        g = torch.Generator(device=device).manual_seed(56)
+        A = torch.log_softmax(torch.randn(S, S, device=device, generator=g), dim=1)
+        init = torch.full((S,), float(np.log(1.0 / S + np.finfo(np.float32).tiny)), device=device)
+        # warm-up on three short prefixes (same kernels, same clocks) instead of three 10^6-frame passes
+        import torbi_b200
+        for _ in range(3):
+            torbi_b200.decode(obs[:, :20000].contiguous(), torch.tensor([20000], dtype=torch.int32), A, init, flags=flags)
+        entry('c5', obs, torch.tensor([T], dtype=torch.int32), A, init, 1, 0,
+              f'config 5: S=4096, B=1, T={T}, dense transition (L2-stream / barrier bound, not FP32 bound); '
+              'warm-up = 3 decodes of a 20000-frame prefix')
+        del obs
+    torch.cuda.empty_cache()
+    return out
 
 
 def bench_graft(args):
@@ -262,6 +416,7 @@ def bench_graft(args):
                          '(use --impl reference for the CPU reference)')
     torch.cuda.set_device(local)
     device = torch.device(f'cuda:{local}')
+    binding = bind_to_gpu_numa_node(local, world)
     if world > 1:
         # NCCL may print its version banner on stdout (NCCL_DEBUG=VERSION on some boxes); the contract is
         # ONE JSON line there, so stdout points at stderr while the communicator comes up
@@ -282,7 +437,14 @@ def bench_graft(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(*values):
+        times = torch.tensor(values, dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        return [float(v) for v in times]
+
     lib = _ffi.library()
+    global_batch_strong = args.batch
     if args.scaling == 'strong':
         if args.batch % world:
             raise SystemExit('--scaling strong needs --batch divisible by the number of ranks')
@@ -291,10 +453,8 @@ def bench_graft(args):
     obs, frames, A, init = make_workload(args, device, 1234 + rank)
     flags = _ffi.EPS_FLOOR | _ffi.TIME_KERNELS
     flags |= {'auto': 0, 'generic': _ffi.FORCE_GENERIC, 'tiled': _ffi.FORCE_TILED, 'wide': _ffi.FORCE_WIDE,
-              'split': _ffi.FORCE_SPLIT}[args.kernel]
+              'split': _ffi.FORCE_SPLIT, 'cluster': _ffi.FORCE_CLUSTER}[args.kernel]
     flags |= {0: 0, 16: _ffi.TILE_ROWS_16, 32: _ffi.TILE_ROWS_32, 64: _ffi.TILE_ROWS_64}[args.tile_rows]
-    if args.ws:
-        flags |= _ffi.TILED_WS
     if args.banded:
         flags |= _ffi.BANDED
     if args.backpointers:
@@ -303,34 +463,10 @@ def bench_graft(args):
         flags |= _ffi.SPLIT_STREAMED
     timesteps_per_step = int(frames.sum())
 
-    fwd_ms, back_ms = [], []
-
-    def step(record):
-        indices = torbi_b200.decode(obs, frames, A, init, flags=flags)
-        if record:
-            import ctypes
-            f, b = ctypes.c_float(), ctypes.c_float()
-            _ffi.check(lib.torbi_b200_last_timing(ctypes.byref(f), ctypes.byref(b)))
-            fwd_ms.append(f.value); back_ms.append(b.value)
-        return indices
-
-    for _ in range(args.warmup):
-        step(False)
-    barrier()
-    launches0 = lib.torbi_b200_launch_count()
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        barrier()
-        start.record()
-        for _ in range(args.steps):
-            indices = step(True)
-        end.record()
-        barrier()
-    elapsed_ms = start.elapsed_time(end)
-    launches = lib.torbi_b200_launch_count() - launches0
-    kernel = lib.torbi_b200_last_kernel().decode()
-    backtrace = lib.torbi_b200_last_backtrace().decode()
-    checksum = int(indices.sum(dtype=torch.int64))
+    main = timed_decode(lib, obs, frames, A, init, flags, args.steps, args.warmup, barrier, local)
+    elapsed_ms = main['elapsed_ms']
+    checksum = main['checksum']
+    kernel, backtrace = main['kernel'], main['backtrace']
 
     # end to end through the C ABI host entry: pinned host buffers
     e2e_ms = None
@@ -355,11 +491,26 @@ def bench_graft(args):
         del host_obs
         lib.torbi_b200_release()
 
-    # max over ranks
-    times = torch.tensor([elapsed_ms, e2e_ms or 0.0], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_max = float(times[0]), float(times[1])
+    # Strong scaling in the same invocation (the conservative reading of "batch 512 at 1/2/4/8 B200",
+    # SURVEY 8d): ONE global batch of 512 sequences, 512 / N per GPU (rank r contributes the first 512 / N
+    # sequences of the batch it already holds); at N = 1 this IS the headline run.
+    strong = None
+    if args.scaling == 'weak' and not args.no_strong and global_batch_strong % world == 0:
+        share = global_batch_strong // world
+        if world == 1:
+            s_run, s_frames = main, frames
+        else:
+            s_obs = obs[:share].contiguous() if share < B else obs
+            s_frames = frames[:share]
+            strong_flags = flags & ~(_ffi.TILE_ROWS_64 | _ffi.TILE_ROWS_32 | _ffi.TILE_ROWS_16) if args.kernel == 'auto' else flags
+            s_run = timed_decode(lib, s_obs, s_frames, A, init, strong_flags, args.steps, args.warmup, barrier, local)
+            del s_obs
+        s_elapsed, = max_over_ranks(s_run['elapsed_ms'])
+        strong = s_run, s_frames, share, s_elapsed
+
+    elapsed_ms, e2e_max = max_over_ranks(elapsed_ms, e2e_ms or 0.0)
+    del obs
+    torch.cuda.empty_cache()
 
     if rank == 0:
         peaks = measured_peaks()
@@ -368,42 +519,60 @@ def bench_graft(args):
         sm_count = torch.cuda.get_device_properties(device).multi_processor_count
         # FP32 max-plus issue roofline: 2*S^2 lane-ops per timestep,
         # peak = SMs x 128 lanes x max SM clock
-        kernel_ms = statistics.mean(fwd_ms)
+        kernel_ms = main['fwd_ms']
         ops = 2.0 * S * S * timesteps_per_step
         achieved = ops / (kernel_ms * 1e-3) / 1e12
-        peak = sm_count * 128 * peaks['sm_max_mhz'] * 1e6 / 1e12
+        peak = fp32_peak(sm_count, peaks)
         # forward kernel: observation read + fp32 score history (or uint16 backpointers) written
         hbm_bytes = (4.0 * S + (4.0 if backtrace == 'backtrace_recompute' else 2.0) * S) * timesteps_per_step
         hbm_achieved = hbm_bytes / (kernel_ms * 1e-3) / 1e9
+        config = workload_config(args, world)
+        config['host_binding'] = binding
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
             'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(args, world),
+            'config': config,
             'e2e': None if e2e_ms is None else {
                 'value': total / (e2e_max * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_max / args.steps,
+                'h2d_gbs_per_gpu': h2d * args.steps / (e2e_max * 1e-3) / 1e9,
                 'api': 'torbi_b200_decode_host (C ABI, pinned host buffers)'},
-            'gpu_launches': int(launches),
-            'clocks': clocks.summary(),
+            'gpu_launches': main['launches'],
+            'clocks': main['clocks'],
             'roofline': {
                 'bound': 'fp32_alu_issue', 'kernel': kernel, 'achieved': achieved, 'peak': peak,
                 'unit': 'T lane-op/s', 'frac': achieved / peak, 'traffic': profiled_traffic(kernel, args, backtrace),
                 'traffic_note': 'DRAM read+write bytes per launch, ncu --set full capture in profiles/ (not live)',
-                'kernel_ms': kernel_ms, 'kernel_share_of_step': kernel_ms * args.steps / elapsed_ms,
-                'backtrace_ms': statistics.mean(back_ms), 'backtrace': backtrace,
+                'kernel_ms': kernel_ms, 'kernel_share_of_step': kernel_ms * args.steps / main['elapsed_ms'],
+                'backtrace_ms': main['back_ms'], 'backtrace': backtrace,
                 'ops_per_launch': ops, 'peak_source': f"{sm_count} SMs x 128 lanes x {peaks['sm_max_mhz']} MHz, {peaks['source']}",
                 'timesteps_per_s_at_peak': peak * 1e12 / (2.0 * S * S),
                 'hbm': {'bound': 'hbm', 'achieved': hbm_achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                         'frac': hbm_achieved / peaks['hbm_gbs'], 'bytes_per_launch': hbm_bytes},
             },
+            'peak_hbm_gb': main['peak_hbm_gb'],
             'checksum': checksum,
         }
+        if strong is not None:
+            s_run, s_frames, share, s_elapsed = strong
+            s_total = int(s_frames.sum()) * args.steps * world
+            line['strong'] = {
+                'value': s_total / (s_elapsed * 1e-3), 'unit': UNIT, 'global_batch': global_batch_strong,
+                'per_gpu_batch': share, 'ms_per_step': s_elapsed / args.steps, 'kernel': s_run['kernel'],
+                'frac': 2.0 * S * S * int(s_frames.sum()) / (s_run['fwd_ms'] * 1e-3) / 1e12 / peak,
+                'kernel_ms': s_run['fwd_ms'], 'backtrace_ms': s_run['back_ms'], 'clocks': s_run['clocks'],
+                'note': 'strong scaling: the SAME global batch of 512 sequences split evenly over the GPUs, '
+                        'device-resident, CUDA events, max over ranks; value = whole-job timesteps/s'}
+        if world == 1 and not args.no_configs:
+            line['configs'] = other_configs(lib, device, local, peaks, sm_count, barrier, args)
         if world == 1 and not args.no_cpu_baseline:
             step_cpu, timesteps, kind, cores, sample = cpu_sample(args, args.cpu_seconds or 15.0)
             seconds = step_cpu()
             line['cpu_baseline'] = {'value': timesteps / seconds, 'unit': UNIT, 'cores': cores,
-                                    'kind': kind, 'sample': sample}
+                                    'kind': kind, 'sample': sample,
+                                    'scope': "the reference's CPU operator only (torbi.decode); its from_probabilities "
+                                             'adds three more CPU passes over the observations (core.py:189-197)'}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TORBI_B200_ABI_VERSION 1
+#define TORBI_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define TORBI_B200_API __attribute__((visibility("default")))
@@ -52,6 +52,12 @@ extern "C" {
  * observation load instead of three extra passes over (B,T,S). */
 #define TORBI_B200_OBS_IS_PROBABILITY (1u << 0) /* x <- logf(x) first (core.py:189-190)        */
 #define TORBI_B200_EPS_FLOOR (1u << 1)          /* x <- logf(expf(x) + FLT_MIN) (core.py:193-197) */
+/* element type of `observation`: default fp32; with one of these it points at IEEE half / bfloat16
+ * elements (2 bytes each, same (batch, frames, states) layout).  The reference casts any input dtype to
+ * fp32 on the host before the copy (core.py:191); here half-precision inputs cross PCIe / HBM at 2 bytes
+ * per element and the kernels upcast in their observation load -- exact, the decode runs in fp32. */
+#define TORBI_B200_OBS_F16 (1u << 4)
+#define TORBI_B200_OBS_BF16 (1u << 5)
 /* kernel selection, for tests and profiling; default 0 lets the library pick */
 #define TORBI_B200_FORCE_GENERIC (1u << 8)      /* one CTA per sequence, any S                 */
 #define TORBI_B200_FORCE_TILED (1u << 9)        /* batch-tiled max-plus kernel                 */
@@ -85,8 +91,14 @@ extern "C" {
 /* with the split kernel: stream the transition block (16 x 40 tiles) even where the resident
  * 32 x 20 shape would fit (states <= 1536); tests / tuning */
 #define TORBI_B200_SPLIT_STREAMED (1u << 18)
-/* use the warp-specialised variant of the tiled kernel (64-row batches, S % 8 == 0) */
-#define TORBI_B200_TILED_WS (1u << 14)
+/* force the cluster split-K kernel: pairs of CTAs (thread-block clusters of 2) share a 32-sequence x
+ * 20-state tile and split its source states 16 ways (8 warps x 2 CTAs); the partial maxima meet through
+ * distributed shared memory (st.shared::cluster + remote mbarrier arrive) and every CTA pair alternates
+ * between the batches of its group, so one batch's score exchange through L2 is hidden behind the
+ * other's max-plus loop.  Score-history mode, dense transitions, states <= 20 x (#SM / 2). */
+#define TORBI_B200_FORCE_CLUSTER (1u << 19)
+/* (bit 14 was the warp-specialised variant of the tiled kernel: measured slower, no longer built;
+ * source and experiment log kept under tools/experiments/ and profiles/r01_ws_experiment.txt) */
 
 TORBI_B200_API int torbi_b200_abi_version(void);
 
@@ -102,12 +114,23 @@ TORBI_B200_API int torbi_b200_device_count(void);
  * Returns 0 on invalid shape. */
 TORBI_B200_API size_t torbi_b200_workspace_bytes(int64_t batch, int64_t frames, int64_t states, uint32_t flags);
 
+/* The same for one concrete call: the library picks the forward kernel from the length profile first
+ * (as torbi_b200_plan does) and sizes the trailing region for it -- uint16 backpointers when the wide or
+ * generic kernel will run (small batches, one long sequence: half of the figure above), fp32 score
+ * history otherwise.  torbi_b200_decode accepts a workspace of this size for the same arguments and the
+ * same `sm_count` (cudaDevAttrMultiProcessorCount of the device it runs on).  Host logic only; 0 on
+ * invalid arguments. */
+TORBI_B200_API size_t torbi_b200_workspace_bytes_planned(const int32_t *batch_frames, int64_t batch,
+                                                         int64_t frames, int64_t states, uint32_t flags,
+                                                         int sm_count);
+
 /*
  * Decode a batch resident in device memory.  Replaces viterbi_decode_cuda
  * (viterbi.cu:309-362); argument meaning follows viterbi.py:5-30.
  *
- *   observation   device (batch, frames, states) fp32, contiguous.  Log
- *                 probabilities, or whatever `flags` says.  Never written.
+ *   observation   device (batch, frames, states) fp32 (fp16 / bf16 with TORBI_B200_OBS_F16 /
+ *                 _BF16), contiguous.  Log probabilities, or whatever `flags` says.
+ *                 Never written.
  *   batch_frames  HOST   (batch,) int32, each in [1, frames]  (the reference
  *                 trusts these, viterbi.cpp:66; here they are validated)
  *   transition    device (states, states) fp32 log-probs, [destination][source]
@@ -125,10 +148,24 @@ TORBI_B200_API size_t torbi_b200_workspace_bytes(int64_t batch, int64_t frames, 
  * The library never allocates or frees device memory in this entry point and
  * is re-entrant across host threads (one per device).
  */
-TORBI_B200_API int torbi_b200_decode(const float *observation, const int32_t *batch_frames,
+TORBI_B200_API int torbi_b200_decode(const void *observation, const int32_t *batch_frames,
                       const float *transition, const float *initial, int64_t batch,
                       int64_t frames, int64_t states, uint32_t flags, int32_t *indices,
                       float *posterior, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * torbi_b200_decode that also hands out intermediate forward scores: `checkpoints` is a device array
+ * (batch, (frames - 1) / checkpoint_every, states) fp32 receiving P_t (viterbi.cpp:102) for
+ * t = checkpoint_every, 2 checkpoint_every, ... of every item (rows with t >= batch_frames[b] are left
+ * untouched).  The reference keeps these internal; they let a long decode (config 5: 4096 states x 10^6
+ * frames, which the reference cannot index, viterbi.cpp:99) be verified segment by segment: a CPU
+ * restatement started from checkpoint k must reproduce checkpoint k+1 and the decoded path in between.
+ */
+TORBI_B200_API int torbi_b200_decode_checkpointed(const void *observation, const int32_t *batch_frames,
+                      const float *transition, const float *initial, int64_t batch,
+                      int64_t frames, int64_t states, uint32_t flags, int32_t *indices,
+                      float *posterior, void *workspace, size_t workspace_bytes, void *stream,
+                      float *checkpoints, int64_t checkpoint_every);
 
 /*
  * Decode a batch resident in HOST memory on one device: host->device copies,
@@ -139,7 +176,7 @@ TORBI_B200_API int torbi_b200_decode(const float *observation, const int32_t *ba
  * This is the entry torbi.from_probabilities(gpu=k) uses for CPU tensors
  * (/root/reference/torbi/core.py:147-191 moves them with .to(device)).
  */
-TORBI_B200_API int torbi_b200_decode_host(const float *observation, const int32_t *batch_frames,
+TORBI_B200_API int torbi_b200_decode_host(const void *observation, const int32_t *batch_frames,
                            const float *transition, const float *initial, int64_t batch,
                            int64_t frames, int64_t states, uint32_t flags, int32_t *indices,
                            float *posterior, int device);
@@ -150,7 +187,7 @@ TORBI_B200_API int torbi_b200_decode_host(const float *observation, const int32_
  * stream per device; no collective -- each device writes its own rows of the
  * caller's `indices`).  devices[i] are CUDA ordinals; n_devices >= 1.
  */
-TORBI_B200_API int torbi_b200_decode_host_multi(const float *observation, const int32_t *batch_frames,
+TORBI_B200_API int torbi_b200_decode_host_multi(const void *observation, const int32_t *batch_frames,
                                  const float *transition, const float *initial,
                                  int64_t batch, int64_t frames, int64_t states,
                                  uint32_t flags, int32_t *indices, float *posterior,

@@ -54,6 +54,39 @@ def build(verbose: bool = False) -> pathlib.Path:
     return REF_SO
 
 
+REF_CUDA_DIR = REF_DIR / 'cuda'
+REF_CUDA_SO = REF_CUDA_DIR / 'torbi_ref_cuda.so'
+
+
+def cuda_available() -> bool:
+    return REF_CUDA_SO.exists()
+
+
+def build_cuda(verbose: bool = False) -> pathlib.Path:
+    """The reference's own CUDA operator (/root/reference/torbi/csrc/cuda/viterbi.cu with ops.cpp),
+    UNMODIFIED, cross-compiled here for sm_100a with the reference's flags (-O3, setup.py:70-72) into
+    oracle/_ref/cuda/.  Only tools/time_reference_cuda.py loads it (in its own process: it registers
+    the same `torbi` operator library as the CPU build) -- it is the kernel-level bar measured
+    beside ours on the same B200, never part of the product."""
+    if not (REFERENCE_CSRC / 'cuda' / 'viterbi.cu').exists():
+        raise FileNotFoundError(f'{REFERENCE_CSRC}/cuda not present; cannot build the reference CUDA op')
+    os.environ['CC'] = '/usr/bin/gcc'
+    os.environ['CXX'] = '/usr/bin/g++'
+    os.environ['TORCH_CUDA_ARCH_LIST'] = '10.0a'
+    from torch.utils.cpp_extension import load
+    REF_CUDA_DIR.mkdir(parents=True, exist_ok=True)
+    load(
+        name='torbi_ref_cuda',
+        sources=[str(REFERENCE_CSRC / 'ops.cpp'), str(REFERENCE_CSRC / 'cuda' / 'viterbi.cu')],
+        extra_cflags=['-O3'],
+        extra_cuda_cflags=['-O3'],
+        with_cuda=True,
+        is_python_module=False,
+        build_directory=str(REF_CUDA_DIR),
+        verbose=verbose)
+    return REF_CUDA_SO
+
+
 _loaded = False
 
 
@@ -71,4 +104,7 @@ def load_ref():
 
 
 if __name__ == '__main__':
-    print(build(verbose='-v' in sys.argv))
+    if 'cuda' in sys.argv:
+        print(build_cuda(verbose='-v' in sys.argv))
+    else:
+        print(build(verbose='-v' in sys.argv))

@@ -177,3 +177,60 @@ def digest(case):
             h.update(str(v.dtype).encode() + str(v.shape).encode() + v.tobytes())
     h.update(str(bool(case['log_probs'])).encode())
     return h.hexdigest()
+
+
+# ---------------------------------------------------------------------------
+# Entropy chunking (reference: /root/reference/torbi/chunk.py:12-85).  Each case is
+# (observation (frames, states) fp32 LOG probabilities, [(min_chunk_size, threshold), ...]).
+# ---------------------------------------------------------------------------
+
+def _chunk_case(seed, frames, states, peaky_share, gain, settings):
+    def make():
+        rng = np.random.default_rng(seed)
+        logits = rng.standard_normal((frames, states))
+        peaky = rng.random(frames) < peaky_share
+        logits[peaky] *= gain
+        return log_softmax(logits), settings
+    return make
+
+
+def _chunk_threshold_hugger(seed, frames, states, threshold):
+    """Frames whose normalised entropy sits within a few fp32 ulp of the threshold: a two-point
+    mixture (one state with mass p, the rest uniform) with p bisected so that H(p) ~ threshold,
+    then nudged frame by frame.  Any evaluation that rounds differently from the reference's
+    torch CPU ops flips decisions here."""
+    def make():
+        rng = np.random.default_rng(seed)
+        lo, hi = 1.0 / states, 1.0 - 1e-9
+        def H(p):
+            q = (1.0 - p) / (states - 1)
+            return -(p * np.log(p) + (states - 1) * q * np.log(q)) / np.log(states)
+        for _ in range(200):
+            mid = 0.5 * (lo + hi)
+            if H(mid) > threshold:
+                lo = mid
+            else:
+                hi = mid
+        p = 0.5 * (lo + hi) * (1.0 + rng.uniform(-3e-7, 3e-7, size=frames))
+        obs = np.empty((frames, states), np.float64)
+        obs[:] = np.log((1.0 - p) / (states - 1))[:, None]
+        obs[np.arange(frames), rng.integers(0, states, frames)] = np.log(p)
+        return obs.astype(np.float32), [(4, threshold), (1, threshold), (37, threshold)]
+    return make
+
+
+CHUNK_CASES = {
+    'chunk_s24': _chunk_case(101, 400, 24, 0.4, 12.0, [(8, 0.5), (25, 0.5), (3, 0.2), (500, 0.5), (1, 0.5)]),
+    'chunk_s1440': _chunk_case(102, 3000, 1440, 0.5, 9.0, [(64, 0.5), (200, 0.35), (16, 0.7)]),
+    'chunk_s5_short': _chunk_case(103, 7, 5, 0.5, 20.0, [(2, 0.5), (1, 0.8), (2, 0.8), (7, 0.5), (8, 0.5)]),
+    'chunk_hugger_s64': _chunk_threshold_hugger(104, 2000, 64, 0.5),
+    'chunk_hugger_s1440': _chunk_threshold_hugger(105, 1500, 1440, 0.5),
+}
+
+
+def chunk_digest(observation, settings):
+    h = hashlib.sha256()
+    observation = np.ascontiguousarray(observation)
+    h.update(str(observation.dtype).encode() + str(observation.shape).encode() + observation.tobytes())
+    h.update(repr([(int(m), float(t)) for m, t in settings]).encode())
+    return h.hexdigest()

@@ -151,6 +151,23 @@ def main():
         print(f'{name:24s} obs{tuple(obs.shape)} indices[0,:8]={indices[0, :8].tolist()}')
 
     assert out['kat/indices'].tolist() == [[1, 2, 2]]      # tests/test_core.py:25
+
+    # (3) entropy chunking: the reference's own torbi.chunk.entropy / split / chunk
+    # (chunk.py:12-85) on log-probability sequences, several (min_chunk_size, threshold) each
+    # (the package re-exports the function `chunk` over its module, torbi/__init__.py:72-78)
+    ref_chunk = sys.modules['torbi.chunk']
+    for name, make in cases.CHUNK_CASES.items():
+        observation, settings = make()
+        out[f'{name}/digest'] = np.array(cases.chunk_digest(observation, settings))
+        x = torch.from_numpy(observation)
+        out[f'{name}/entropy'] = ref_chunk.entropy(x.T).numpy()
+        for k, (min_chunk, threshold) in enumerate(settings):
+            points = ref_chunk.split(x, min_chunk_size=min_chunk, entropy_threshold=threshold)
+            pieces = ref_chunk.chunk(x, min_chunk_size=min_chunk, entropy_threshold=threshold)
+            assert [int(p.shape[0]) for p in pieces] == \
+                list(np.diff([0] + [int(p) for p in points] + [observation.shape[0]]))
+            out[f'{name}/split{k}'] = np.array(points, dtype=np.int64)
+            print(f'{name:24s} min_chunk={min_chunk:4d} thr={threshold} -> {len(points)} split points')
     np.savez_compressed(HERE / 'golden.npz', **out)
     shutil.rmtree(scratch, ignore_errors=True)
     print('wrote', HERE / 'golden.npz', (HERE / 'golden.npz').stat().st_size, 'bytes')

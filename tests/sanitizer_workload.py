@@ -28,7 +28,8 @@ for (B, T, S) in [(5, 6, 200), (70, 4, 96), (3, 5, 333)]:
                        ('tiled64 backpointers', _ffi.TILE_ROWS_64 | _ffi.BACKPOINTERS),
                        ('tiled16 backpointers', _ffi.TILE_ROWS_16 | _ffi.BACKPOINTERS),
                        ('banded', _ffi.BANDED | _ffi.TILE_ROWS_64), ('banded16', _ffi.BANDED | _ffi.TILE_ROWS_16),
-                       ('banded backpointers', _ffi.BANDED | _ffi.BACKPOINTERS), ('split', _ffi.FORCE_SPLIT), ('split streamed', _ffi.FORCE_SPLIT | _ffi.SPLIT_STREAMED)]:
+                       ('banded backpointers', _ffi.BANDED | _ffi.BACKPOINTERS), ('split', _ffi.FORCE_SPLIT), ('split streamed', _ffi.FORCE_SPLIT | _ffi.SPLIT_STREAMED),
+                       ('cluster', _ffi.FORCE_CLUSTER)]:
         got = torbi_b200.decode(torch.from_numpy(obs).cuda(), torch.from_numpy(frames), torch.from_numpy(A).cuda(),
                                 torch.from_numpy(init).cuda(), flags=flag | _ffi.EPS_FLOOR)
         torch.cuda.synchronize()

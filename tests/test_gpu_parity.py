@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 KERNELS = {'auto': 0, 'generic': _ffi.FORCE_GENERIC, 'tiled16': _ffi.TILE_ROWS_16,
            'tiled32': _ffi.TILE_ROWS_32, 'tiled64': _ffi.TILE_ROWS_64, 'wide': _ffi.FORCE_WIDE,
-           'tiled64ws': _ffi.TILE_ROWS_64 | _ffi.TILED_WS, 'banded': _ffi.BANDED,
+           'banded': _ffi.BANDED,
            'banded16': _ffi.BANDED | _ffi.TILE_ROWS_16,
            # the tiled kernel's backpointer mode (default is score history + recomputed backtrace)
            'tiled64bp': _ffi.TILE_ROWS_64 | _ffi.BACKPOINTERS, 'tiled16bp': _ffi.TILE_ROWS_16 | _ffi.BACKPOINTERS,

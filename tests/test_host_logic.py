@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 import torch
 
+import cases
 import torbi_b200
 from torbi_b200 import _ffi
 
@@ -30,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_flag_values_match_header():
     header = (ROOT / 'include' / 'torbi_b200.h').read_text()
     for name in ('OBS_IS_PROBABILITY', 'EPS_FLOOR', 'FORCE_GENERIC', 'FORCE_TILED', 'FORCE_WIDE', 'TIME_KERNELS',
-                 'TILED_WS', 'BANDED', 'BACKPOINTERS', 'FORCE_SPLIT', 'SPLIT_STREAMED'):
+                 'BANDED', 'BACKPOINTERS', 'FORCE_SPLIT', 'SPLIT_STREAMED'):
         shift = int(re.search(rf'#define TORBI_B200_{name} \(1u << (\d+)\)', header).group(1))
         assert getattr(_ffi, name) == 1 << shift
     for name, value in (('TILE_ROWS_16', 1), ('TILE_ROWS_32', 2), ('TILE_ROWS_64', 3)):
@@ -74,7 +75,6 @@ def test_kernel_plan_host_logic():
     assert plan(full, 2000, 1440, _ffi.FORCE_SPLIT) == 'forward_split'
     assert plan(full, 2000, 1440, _ffi.FORCE_SPLIT | _ffi.BACKPOINTERS) is None
     assert plan(full, 2000, 1440, _ffi.BANDED) == 'forward_tiled_banded'
-    assert plan(full, 2000, 1440, _ffi.TILED_WS) == 'forward_tiled_ws'
     assert plan(full, 2000, 1440, _ffi.FORCE_GENERIC) == 'forward_generic'
     assert plan(full, 2000, 1440, _ffi.TILE_ROWS_16) == 'forward_tiled_16'
     # ragged, heavy tailed: smaller tiles shorten the critical path of the longest items
@@ -154,37 +154,25 @@ def test_collate_and_separate():
         torbi_b200.data.collate([])
 
 
-def reference_split(observation, min_chunk_size, entropy_threshold):
-    """/root/reference/torbi/chunk.py:57-78 spelled out as a plain loop."""
-    x = observation.T
-    ent = -((torch.exp(x) * x).sum(dim=0) / torch.log(torch.tensor(x.shape[0])))
-    cand = ent < entropy_threshold
-    points, i = [], min_chunk_size
-    while i < x.shape[-1]:
-        if cand[i] and cand[i - 1]:
-            points.append(i)
-            i += min_chunk_size
-        else:
-            i += 1
-    return points
-
-
-def test_chunk_matches_reference_rule():
-    g = torch.Generator().manual_seed(1234)
-    frames, states = 400, 24
-    logits = torch.randn(frames, states, generator=g)
-    peaky = torch.rand(frames, generator=g) < 0.4
-    logits[peaky] *= 12.0
-    observation = torch.log_softmax(logits, dim=-1)
-    for min_chunk, threshold in [(8, 0.5), (25, 0.5), (3, 0.2), (500, 0.5)]:
-        expected = reference_split(observation, min_chunk, threshold)
-        assert torbi_b200.chunk.__module__  # module import sanity
-        from torbi_b200.chunk import split
-        assert split(observation, min_chunk, threshold) == expected
-        chunks = torbi_b200.chunk(observation, min_chunk, threshold)
-        assert len(chunks) == len(expected) + 1
-        assert torch.equal(torch.cat(chunks), observation)
-        assert all(c.shape[0] >= min(min_chunk, frames) for c in chunks[:-1])
+@pytest.mark.parametrize('name', list(cases.CHUNK_CASES))
+def test_chunk_matches_reference_golden(name, golden):
+    """Split points, framewise entropy and chunk views against what the reference's OWN
+    torbi.chunk.split / entropy / chunk returned (tests/golden/make_golden.py imports the
+    reference package; /root/reference/torbi/chunk.py:12-85)."""
+    import importlib
+    chunk_module = importlib.import_module('torbi_b200.chunk')   # (the package re-exports the function over the module)
+    observation, settings = cases.CHUNK_CASES[name]()
+    assert cases.chunk_digest(observation, settings) == str(golden[f'{name}/digest'])
+    x = torch.from_numpy(observation)
+    entropy = chunk_module.entropy(x.T).numpy()
+    assert np.array_equal(entropy.view(np.int32), golden[f'{name}/entropy'].view(np.int32))
+    for k, (min_chunk, threshold) in enumerate(settings):
+        expected = golden[f'{name}/split{k}'].tolist()
+        assert chunk_module.split(x, min_chunk, threshold) == expected
+        chunks = torbi_b200.chunk(x, min_chunk, threshold)
+        assert [int(c.shape[0]) for c in chunks] == np.diff([0] + expected + [x.shape[0]]).tolist()
+        assert torch.equal(torch.cat(chunks), x)
+        assert all(c.data_ptr() == x[b].data_ptr() for c, b in zip(chunks, [0] + expected))   # views
 
 
 def test_cli_and_configure(tmp_path):
@@ -343,3 +331,108 @@ def test_native_reader_rejects_damaged_files(tmp_path):
     infos = native.inspect([tmp_path / name for name in cases_] + [good])
     assert all(info.status != 0 for info in infos[:-1]), [info.status for info in infos]
     assert infos[-1].status == 0
+
+
+def test_planned_workspace_follows_the_kernel_choice():
+    """torbi_b200_workspace_bytes_planned sizes the trailing region for the kernel the call will
+    use: uint16 backpointers (2 bytes per entry) for the wide / generic kernels, fp32 score history
+    (4 bytes) for the tiled / split / cluster kernels.  Config 5 needs 8.3 GB, not 16.5 GB."""
+    lib = _ffi.library()
+
+    def planned(frames, T, S, flags=0, sm_count=148):
+        frames = np.ascontiguousarray(frames, dtype=np.int32)
+        return lib.torbi_b200_workspace_bytes_planned(frames.ctypes.data, len(frames), T, S, flags, sm_count)
+
+    upper = lib.torbi_b200_workspace_bytes(1, 1_000_000, 4096, 0)
+    exact = planned([1_000_000], 1_000_000, 4096)
+    assert plan([1_000_000], 1_000_000, 4096) == 'forward_wide'
+    assert upper - exact == 2 * 1_000_000 * 4096 and exact < 8.3e9
+    assert planned([2000] * 512, 2000, 1440) == lib.torbi_b200_workspace_bytes(512, 2000, 1440, 0)
+    assert planned([2000] * 64, 2000, 1440, _ffi.FORCE_CLUSTER) == lib.torbi_b200_workspace_bytes(64, 2000, 1440, 0)
+    assert planned([4, 4], 4, 20000) == lib.torbi_b200_workspace_bytes(2, 4, 20000, _ffi.BACKPOINTERS)
+    assert planned([4, 9], 4, 100) == 0 and 'outside' in _ffi.last_error()
+    assert planned([4], 4, 100, _ffi.OBS_F16 | _ffi.OBS_BF16) == 0
+
+
+def test_cluster_kernel_plan():
+    assert plan([2000] * 64, 2000, 1440, _ffi.FORCE_CLUSTER) == 'forward_cluster'
+    assert plan([2000] * 512, 2000, 1480, _ffi.FORCE_CLUSTER) == 'forward_cluster'      # 74 pairs = 148 SMs
+    assert plan([2000] * 64, 2000, 1481, _ffi.FORCE_CLUSTER) is None                     # 75 pairs do not fit
+    assert plan([2000] * 64, 2000, 1440, _ffi.FORCE_CLUSTER | _ffi.BACKPOINTERS) is None
+    assert plan([2000] * 64, 2000, 1440, _ffi.FORCE_CLUSTER | _ffi.BANDED) is None
+    # the banded flag is a hint: dropped where the tiled kernel cannot run
+    assert plan([3] * 32, 3, 12000, _ffi.BANDED) == plan([3] * 32, 3, 12000)
+    assert plan([3] * 32, 3, 12000, _ffi.BANDED | _ffi.FORCE_TILED) is None
+
+
+def test_torbi_alias_package():
+    """`import torbi` is torbi_b200 (the reference's call sites run unchanged,
+    /root/reference/torbi/__init__.py:72-78)."""
+    import importlib
+    import sys
+    saved = {name: module for name, module in sys.modules.items() if name == 'torbi' or name.startswith('torbi.')}
+    for name in saved:
+        del sys.modules[name]
+    try:
+        torbi = importlib.import_module('torbi')
+        assert torbi is torbi_b200
+        for name in ('from_probabilities', 'from_file', 'from_file_to_file', 'from_files_to_files', 'from_dataloader',
+                     'decode', 'chunk', 'data', 'BATCH_SIZE', 'MIN_CHUNK_SIZE', 'ENTROPY_THRESHOLD'):
+            assert hasattr(torbi, name), name
+        assert importlib.import_module('torbi.core') is importlib.import_module('torbi_b200.core')
+        assert importlib.import_module('torbi.data').loader is torbi_b200.data.loader
+    finally:
+        for name in [n for n in sys.modules if n == 'torbi' or n.startswith('torbi.')]:
+            del sys.modules[name]
+        sys.modules.update(saved)
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16, torch.float32])
+def test_native_reader_keeps_half_precision_files(tmp_path, dtype):
+    """fp16 / bf16 posteriorgram files are read natively into a batch of their own dtype (2 bytes per
+    element up to the kernel's observation load); mixed dtypes go to the generic collate."""
+    from torbi_b200.data import native
+    g = torch.Generator().manual_seed(3)
+    tensors = [torch.randn(n, 12, generator=g).to(dtype) for n in (5, 9, 1)]
+    files = []
+    for i, tensor in enumerate(tensors):
+        files.append(tmp_path / f'{i}.pt')
+        torch.save(tensor, files[-1])
+    pinned_like = torch.empty(1000, dtype=torch.float32)
+    for out in (None, pinned_like):
+        observation, frames = native.load_batch(files, threads=2, out=out)
+        assert observation.dtype == dtype and observation.shape == (3, 9, 12) and frames.tolist() == [5, 9, 1]
+        for i, tensor in enumerate(tensors):
+            assert torch.equal(observation[i, :tensor.shape[0]], tensor)
+            assert (observation[i, tensor.shape[0]:] == 0).all()
+    torch.save(tensors[0].to(torch.float64), files[0])
+    assert native.load_batch(files, threads=2) is None
+
+
+def test_file_pipeline_stops_its_loader_when_the_decode_fails(tmp_path, monkeypatch):
+    """A failing decode must not leave the loader thread blocked on its queue holding pinned buffers."""
+    import threading
+    from torbi_b200 import core
+    files = []
+    for i in range(12):
+        files.append(str(tmp_path / f'{i}.pt'))
+        torch.save(torch.rand(4, 6), files[-1])
+    monkeypatch.setattr(torbi_b200, 'BATCH_SIZE', 2)
+
+    def boom(**kwargs):
+        raise RuntimeError('decode failed')
+    monkeypatch.setattr(core, 'from_probabilities', boom)
+    before = threading.active_count()
+    with pytest.raises(RuntimeError, match='decode failed'):
+        core._from_files_native(files, [100] * len(files), {f: f + '.out' for f in files}, None, None, True, 0,
+                                False, 2)
+    assert threading.active_count() == before
+
+    def failing_loader():
+        yield torch.zeros(1, 2, 3), torch.tensor([2]), [1], ['a']
+        yield torch.zeros(1, 2, 3), torch.tensor([2]), [1], ['b']
+        yield torch.zeros(1, 2, 3), torch.tensor([2]), [1], ['c']
+    iterator = core._prefetched(failing_loader(), 1)
+    next(iterator)
+    iterator.close()                                               # consumer walks away early
+    assert threading.active_count() == before

@@ -1,3 +1,5 @@
+// EXPERIMENT, not built into libtorbi_b200.so: warp-specialised variant of the tiled kernel (round 1).
+// Measured slower than the classic kernel (profiles/r01_ws_experiment.txt); kept as the record of the A/B.
 // Warp-specialised variant of the batch-tiled forward kernel (forward_tiled.cu)
 // for full 64-sequence batches.  Same tiling, same arithmetic, same results; the
 // difference is WHO does what, so that nothing but the max-plus inner loop sits on

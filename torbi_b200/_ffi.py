@@ -21,6 +21,8 @@ ERR_OUT_OF_MEMORY = -4
 
 OBS_IS_PROBABILITY = 1 << 0
 EPS_FLOOR = 1 << 1
+OBS_F16 = 1 << 4
+OBS_BF16 = 1 << 5
 FORCE_GENERIC = 1 << 8
 FORCE_TILED = 1 << 9
 TIME_KERNELS = 1 << 10
@@ -28,13 +30,13 @@ FORCE_WIDE = 1 << 11
 TILE_ROWS_16 = 1 << 12
 TILE_ROWS_32 = 2 << 12
 TILE_ROWS_64 = 3 << 12
-TILED_WS = 1 << 14
 BANDED = 1 << 15
 BACKPOINTERS = 1 << 16
 FORCE_SPLIT = 1 << 17
 SPLIT_STREAMED = 1 << 18
+FORCE_CLUSTER = 1 << 19
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _p = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -46,6 +48,9 @@ SIGNATURES = {
     'torbi_b200_workspace_bytes': (ctypes.c_size_t, [_i64, _i64, _i64, ctypes.c_uint32]),
     'torbi_b200_decode': (ctypes.c_int, [
         _p, _p, _p, _p, _i64, _i64, _i64, ctypes.c_uint32, _p, _p, _p, ctypes.c_size_t, _p]),
+    'torbi_b200_workspace_bytes_planned': (ctypes.c_size_t, [_p, _i64, _i64, _i64, ctypes.c_uint32, ctypes.c_int]),
+    'torbi_b200_decode_checkpointed': (ctypes.c_int, [
+        _p, _p, _p, _p, _i64, _i64, _i64, ctypes.c_uint32, _p, _p, _p, ctypes.c_size_t, _p, _p, _i64]),
     'torbi_b200_decode_host': (ctypes.c_int, [
         _p, _p, _p, _p, _i64, _i64, _i64, ctypes.c_uint32, _p, _p, ctypes.c_int]),
     'torbi_b200_decode_host_multi': (ctypes.c_int, [

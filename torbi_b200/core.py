@@ -114,7 +114,10 @@ def _prepare_observation(observation, log_probs, device, mode):
             else:
                 # the reference takes the log in the INPUT dtype, then casts (core.py:190-191)
                 observation = torch.log(observation)
-        return observation.to(device=device, dtype=torch.float32), flags
+        # fp16 / bf16 observations travel and stay as 2-byte elements; the kernels upcast in their
+        # observation load, which is what the reference's .to(float32) does (core.py:191), exactly
+        dtype = observation.dtype if observation.dtype in (torch.float16, torch.bfloat16) else torch.float32
+        return observation.to(device=device, dtype=dtype), flags
     if mode == 'host':
         # exactly the reference's CPU ops, then one host->device copy
         observation = observation.detach().to('cpu')
@@ -451,12 +454,25 @@ def _from_files_native(input_files, sizes, mapping, transition, initial, log_pro
         free.put(torch.empty(numel, dtype=torch.float32, pin_memory=pin))
     ready: queue.Queue = queue.Queue(maxsize=depth)
     done = object()
+    stop = threading.Event()          # set when the consumer gives up: the producer must not block for ever
+
+    def handoff(q, item=None, get=False):
+        """put / get that gives up once `stop` is set"""
+        while not stop.is_set():
+            try:
+                return (q.get(timeout=0.2),) if get else q.put(item, timeout=0.2) or (None,)
+            except (queue.Empty, queue.Full):
+                continue
+        return None
 
     def produce():
         try:
             for batch in batches:
                 files = [input_files[i] for i in batch]
-                buffer = free.get()
+                got = handoff(free, get=True)
+                if got is None:
+                    return
+                buffer = got[0]
                 loaded = native_io.load_batch(files, threads=io_threads, out=buffer)
                 if loaded is None:
                     # mixed dtypes / widths: the reference's own collate (file dtype kept, cast later)
@@ -464,12 +480,14 @@ def _from_files_native(input_files, sizes, mapping, transition, initial, log_pro
                     observation, batch_frames, _, _ = torbi_b200.data.collate(
                         [dataset[i] for i in range(len(files))], pin_memory=pin)
                     loaded = (observation, batch_frames)
-                ready.put((loaded[0], loaded[1], files, buffer))
-            ready.put(done)
+                if handoff(ready, (loaded[0], loaded[1], files, buffer)) is None:
+                    return
+            handoff(ready, done)
         except BaseException as error:  # noqa: BLE001 - re-raised by the consumer
-            ready.put(error)
+            handoff(ready, error)
 
-    threading.Thread(target=produce, daemon=True).start()
+    producer = threading.Thread(target=produce, daemon=True)
+    producer.start()
 
     if transition is not None:
         log_transition = transition if log_probs else torch.log(transition)
@@ -505,6 +523,10 @@ def _from_files_native(input_files, sizes, mapping, transition, initial, log_pro
         for future in pending:
             future.result()
     finally:
+        # a failed decode / save must not leave the loader thread blocked on a full queue holding
+        # pinned batch buffers: tell it to stop, then wait for it
+        stop.set()
+        producer.join()
         saver.shutdown(wait=True)
         if bar is not None:
             bar.close()
@@ -530,25 +552,41 @@ def _prefetched(dataloader, depth):
         return
     batches: queue.Queue = queue.Queue(maxsize=depth)
     done = object()
+    stop = threading.Event()          # set when the consumer stops iterating (error, early exit)
+
+    def put(item):
+        while not stop.is_set():
+            try:
+                batches.put(item, timeout=0.2)
+                return True
+            except queue.Full:
+                continue
+        return False
 
     def produce():
         try:
             for observation, batch_frames, batch_chunks, files in dataloader:
                 if torch.cuda.is_available() and not observation.is_pinned():
                     observation = observation.pin_memory()
-                batches.put((observation, batch_frames, batch_chunks, files))
-            batches.put(done)
+                if not put((observation, batch_frames, batch_chunks, files)):
+                    return
+            put(done)
         except BaseException as error:  # noqa: BLE001 - re-raised by the consumer
-            batches.put(error)
+            put(error)
 
-    threading.Thread(target=produce, daemon=True).start()
-    while True:
-        item = batches.get()
-        if item is done:
-            return
-        if isinstance(item, BaseException):
-            raise item
-        yield item
+    producer = threading.Thread(target=produce, daemon=True)
+    producer.start()
+    try:
+        while True:
+            item = batches.get()
+            if item is done:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+    finally:
+        stop.set()
+        producer.join()
 
 
 def from_dataloader(

@@ -149,30 +149,38 @@ int torbi_b200_device_count(void) {
 
 size_t torbi_b200_workspace_bytes(int64_t B, int64_t T, int64_t S, uint32_t flags) {
     if (validate_shape(B, T, S) != TORBI_B200_OK) return 0;
-    return carve_workspace(nullptr, B, T, S, flags).bytes;
+    return carve_workspace(nullptr, B, T, S, workspace_has_history(flags)).bytes;
 }
 
 }  // extern "C"
 
 namespace {
 
-enum Choice { kGeneric, kTiled, kWide, kSplit };
+enum Choice { kGeneric, kTiled, kWide, kSplit, kCluster };
+// whether the cost model may pick the cluster kernel by itself (else only TORBI_B200_FORCE_CLUSTER does)
+constexpr bool kClusterAuto = false;
 
-// Kernel selection: estimated time of the batch-tiled and the wide decomposition for this
-// length profile (longest-first `order`), unless a flag forces one.  Also fixes a.tile_rows.
-int choose_kernel(ForwardArgs &a, const int32_t *batch_frames, const std::vector<int32_t> &order,
-                  uint32_t flags, Choice *out) {
+// Kernel selection: estimated time of the batch-tiled, split-K, cluster and wide decompositions for
+// this length profile (`sorted` = batch_frames, longest first), unless a flag forces one.  Also fixes
+// a.tile_rows.  `flags` may lose TORBI_B200_BANDED (a hint) where the tiled kernel cannot run.
+int choose_kernel(ForwardArgs &a, const std::vector<int32_t> &sorted, uint32_t &flags, Choice *out) {
     const int64_t B = a.B, S = a.S;
-    std::vector<int32_t> sorted(B);
-    for (int64_t i = 0; i < B; ++i) sorted[i] = batch_frames[order[i]];
     double tiled_seconds = 0.0;
     a.tile_rows = tiled_choose_rows(sorted.data(), B, S, a.sm_count, &tiled_seconds);
     if (flags & TORBI_B200_TILE_ROWS_MASK)
         a.tile_rows = 16 << (((flags & TORBI_B200_TILE_ROWS_MASK) >> 12) - 1);
     const bool can_tile = forward_tiled_supported(a), can_wide = forward_wide_supported(a);
-    // the split-K small-tile kernel exists in score-history mode only, dense transitions only
-    const bool can_split = forward_split_supported(a) && workspace_has_history(flags) &&
-                           !(flags & (TORBI_B200_BANDED | TORBI_B200_TILED_WS));
+    // TORBI_B200_BANDED is a speed hint (results are identical either way): where the tiled kernel cannot
+    // run (more destination tiles than SMs, i.e. S > 80 x #SM) the flag is dropped and the selection
+    // proceeds as without it.  Only FORCE_TILED / TILE_ROWS_* insist on the tiled kernel.
+    if ((flags & TORBI_B200_BANDED) && !can_tile) {
+        flags &= ~TORBI_B200_BANDED;
+        a.flags = flags;
+    }
+    // the split-K kernels exist in score-history mode only, dense transitions only
+    const bool history_ok = workspace_has_history(flags) && !(flags & TORBI_B200_BANDED);
+    const bool can_split = forward_split_supported(a) && history_ok;
+    const bool can_cluster = forward_cluster_supported(a) && history_ok;
     Choice choice = kGeneric;
     double best_seconds = 1e300;
     if (can_tile) { choice = kTiled; best_seconds = tiled_seconds; }
@@ -180,11 +188,20 @@ int choose_kernel(ForwardArgs &a, const int32_t *batch_frames, const std::vector
         const double seconds = split_estimate_seconds(sorted.data(), B, S, a.sm_count);
         if (seconds < best_seconds) { choice = kSplit; best_seconds = seconds; }
     }
+    if (can_cluster && kClusterAuto) {
+        const double seconds = cluster_estimate_seconds(sorted.data(), B, S, a.sm_count);
+        if (seconds < best_seconds) { choice = kCluster; best_seconds = seconds; }
+    }
     if (can_wide && wide_estimate_seconds(sorted.data(), B, S, a.sm_count) < best_seconds) choice = kWide;
     if (flags & TORBI_B200_FORCE_SPLIT) {
         if (!can_split)
             return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "split kernel does not support this shape / these flags");
         choice = kSplit;
+    }
+    if (flags & TORBI_B200_FORCE_CLUSTER) {
+        if (!can_cluster)
+            return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "cluster kernel does not support this shape / these flags");
+        choice = kCluster;
     }
     if (flags & (TORBI_B200_FORCE_TILED | TORBI_B200_TILE_ROWS_MASK | TORBI_B200_BANDED)) {
         if (!can_tile) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "tiled kernel does not support this shape");
@@ -199,79 +216,137 @@ int choose_kernel(ForwardArgs &a, const int32_t *batch_frames, const std::vector
     return TORBI_B200_OK;
 }
 
-const char *kernel_name(const ForwardArgs &a, Choice choice, uint32_t flags) {
-    if (choice == kTiled && (flags & TORBI_B200_TILED_WS) && !(flags & TORBI_B200_BANDED) &&
-        forward_tiled_ws_supported(a))
-        return "forward_tiled_ws";
+const char *kernel_name(int tile_rows, Choice choice, uint32_t flags) {
     if (choice == kTiled) {
         if (flags & TORBI_B200_BANDED)
-            return a.tile_rows == 64 ? "forward_tiled_banded" : a.tile_rows == 32 ? "forward_tiled_banded_32" : "forward_tiled_banded_16";
-        return a.tile_rows == 64 ? "forward_tiled" : a.tile_rows == 32 ? "forward_tiled_32" : "forward_tiled_16";
+            return tile_rows == 64 ? "forward_tiled_banded" : tile_rows == 32 ? "forward_tiled_banded_32" : "forward_tiled_banded_16";
+        return tile_rows == 64 ? "forward_tiled" : tile_rows == 32 ? "forward_tiled_32" : "forward_tiled_16";
     }
     if (choice == kSplit) return "forward_split";
+    if (choice == kCluster) return "forward_cluster";
     return choice == kWide ? "forward_wide" : "forward_generic";
 }
 
-// torbi_b200_decode plus `frames_ready`: a device word the forward kernel polls
-// when the observations are still being copied in (host entry); nullptr otherwise.
-// `*streamed` reports whether the chosen kernel honours it.
-int decode_device(const float *observation, const int32_t *batch_frames,
-                  const float *transition, const float *initial, int64_t B, int64_t T,
-                  int64_t S, uint32_t flags, int32_t *indices, float *posterior,
-                  void *workspace, size_t workspace_bytes, void *stream_,
-                  const int32_t *frames_ready, bool *streamed) {
-    g_error[0] = 0;
+// Everything about a call that is decided on the host before anything is enqueued: validated
+// lengths, the longest-first order, the kernel, and whether the workspace tail holds the fp32 score
+// history (4 bytes per (b,t,s)) or uint16 backpointers (2 bytes).
+struct Plan {
+    Choice choice = kGeneric;
+    int tile_rows = 64;
+    uint32_t flags = 0;          // caller's flags, minus hints that do not apply
+    bool history = false;
+    int64_t max_frames = 0;
+    std::vector<int32_t> order;  // (pad_batch,) items longest first, -1 = empty slot
+    size_t workspace_bytes = 0;
+};
+
+int make_plan(const int32_t *batch_frames, int64_t B, int64_t T, int64_t S, uint32_t flags, int sm_count,
+              Plan *plan) {
     int rc = validate_shape(B, T, S);
     if (rc) return rc;
-    if (!observation || !batch_frames || !transition || !initial || !indices || !workspace)
-        return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "NULL pointer argument");
-    int64_t max_frames = 0;
+    if (!batch_frames) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+    if ((flags & TORBI_B200_OBS_F16) && (flags & TORBI_B200_OBS_BF16))
+        return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "TORBI_B200_OBS_F16 and TORBI_B200_OBS_BF16 are exclusive");
+    plan->max_frames = 0;
     for (int64_t b = 0; b < B; ++b) {
         // the reference trusts these and reads out of bounds for 0 (viterbi.cpp:152)
         if (batch_frames[b] < 1 || batch_frames[b] > T)
             return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "batch_frames[%lld] = %d outside [1, %lld]",
                         (long long)b, batch_frames[b], (long long)T);
-        max_frames = std::max<int64_t>(max_frames, batch_frames[b]);
+        plan->max_frames = std::max<int64_t>(plan->max_frames, batch_frames[b]);
     }
-    if (reinterpret_cast<uintptr_t>(workspace) % 256)
-        return fail(TORBI_B200_ERR_WORKSPACE, "workspace must be 256-byte aligned");
-    Workspace ws = carve_workspace(workspace, B, T, S, flags);
-    if (workspace_bytes < ws.bytes)
-        return fail(TORBI_B200_ERR_WORKSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, ws.bytes);
+    plan->order.assign(pad_batch(B), -1);
+    std::iota(plan->order.begin(), plan->order.begin() + B, 0);
+    std::stable_sort(plan->order.begin(), plan->order.begin() + B,
+                     [&](int32_t x, int32_t y) { return batch_frames[x] > batch_frames[y]; });
+    std::vector<int32_t> sorted(B);
+    for (int64_t i = 0; i < B; ++i) sorted[i] = batch_frames[plan->order[i]];
+    ForwardArgs a{};
+    a.B = B; a.T = T; a.S = S;
+    a.flags = flags;
+    a.sm_count = sm_count;
+    // layout only, never dereferenced: the `supported` predicates only look at shapes
+    a.ws = carve_workspace(reinterpret_cast<void *>(uintptr_t(256)), B, T, S, workspace_has_history(flags));
+    a.observation = reinterpret_cast<const float *>(uintptr_t(256));
+    rc = choose_kernel(a, sorted, flags, &plan->choice);
+    if (rc) return rc;
+    plan->flags = flags;
+    plan->tile_rows = a.tile_rows;
+    plan->history = plan->choice == kSplit || plan->choice == kCluster ||
+                    (plan->choice == kTiled && workspace_has_history(flags));
+    plan->workspace_bytes = carve_workspace(nullptr, B, T, S, plan->history).bytes;
+    return TORBI_B200_OK;
+}
 
+struct DecodeOptions {
+    // device word the forward kernel polls when the observations are still being copied in (host
+    // entry); nullptr otherwise.  `*streamed` reports whether the chosen kernel honours it.
+    const int32_t *frames_ready = nullptr;
+    bool *streamed = nullptr;
+    // device (B, (T - 1) / every, S): forward scores P_t for t = every, 2 every, ... (t < frames_b)
+    float *checkpoints = nullptr;
+    int64_t checkpoint_every = 0;
+    const Plan *plan = nullptr;  // made by the caller already (host entry)
+};
+
+int decode_device(const void *observation, const int32_t *batch_frames,
+                  const float *transition, const float *initial, int64_t B, int64_t T,
+                  int64_t S, uint32_t flags, int32_t *indices, float *posterior,
+                  void *workspace, size_t workspace_bytes, void *stream_, const DecodeOptions &opt) {
+    g_error[0] = 0;
+    if (!observation || !batch_frames || !transition || !initial || !indices || !workspace)
+        return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "NULL pointer argument");
     int device = 0;
     cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
     DeviceInfo info;
-    rc = device_info(device, &info);
+    int rc = device_info(device, &info);
     if (rc) return rc;
+    Plan own_plan;
+    if (!opt.plan) {
+        rc = make_plan(batch_frames, B, T, S, flags, info.sm_count, &own_plan);
+        if (rc) return rc;
+    }
+    const Plan &plan = opt.plan ? *opt.plan : own_plan;
+    flags = plan.flags;
+    if (opt.checkpoints && opt.checkpoint_every < 1)
+        return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "checkpoint_every must be >= 1");
+    if (reinterpret_cast<uintptr_t>(workspace) % 256)
+        return fail(TORBI_B200_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    // the kernel is chosen first, so a call that ends up on the wide / generic kernel (uint16
+    // backpointers) only needs half the trailing region of a score-history call
+    Workspace ws = carve_workspace(workspace, B, T, S, plan.history);
+    if (workspace_bytes < ws.bytes)
+        return fail(TORBI_B200_ERR_WORKSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, ws.bytes);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
     // lengths and the longest-first processing order go to the device
-    std::vector<int32_t> order(pad_batch(B), -1);
-    std::iota(order.begin(), order.begin() + B, 0);
-    std::stable_sort(order.begin(), order.begin() + B,
-                     [&](int32_t x, int32_t y) { return batch_frames[x] > batch_frames[y]; });
     e = cudaMemcpyAsync(ws.frames, batch_frames, sizeof(int32_t) * B, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(ws.order, order.data(), sizeof(int32_t) * order.size(),
+        e = cudaMemcpyAsync(ws.order, plan.order.data(), sizeof(int32_t) * plan.order.size(),
                             cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(ws.sync, 0, sizeof(uint32_t) * kSyncWords, stream);
     if (e != cudaSuccess) return fail_cuda(e, "stage batch_frames");
-    // `order` is pageable host memory: the async copy has been staged by the
-    // time cudaMemcpyAsync returns, so the vector may go out of scope.
+    // (pageable host memory: the async copies have been staged by the time cudaMemcpyAsync returns)
 
     ForwardArgs a{};
-    a.observation = observation;
+    a.observation = static_cast<const float *>(observation);
+    a.obs_dtype = (flags & TORBI_B200_OBS_F16) ? 1 : (flags & TORBI_B200_OBS_BF16) ? 2 : 0;
     a.transition = transition;
     a.initial = initial;
     a.posterior = posterior;
     a.B = B; a.T = T; a.S = S;
-    a.max_frames = max_frames;
+    a.max_frames = plan.max_frames;
     a.flags = flags;
     a.sm_count = info.sm_count;
+    a.tile_rows = plan.tile_rows;
     a.ws = ws;
-    a.frames_ready = frames_ready;
+    a.frames_ready = opt.frames_ready;
+    a.checkpoints = opt.checkpoints;
+    a.checkpoint_every = opt.checkpoints ? opt.checkpoint_every : 0;
+    if (opt.checkpoints && plan.choice == kTiled && !plan.history)
+        return fail(TORBI_B200_ERR_INVALID_ARGUMENT,
+                    "checkpoints are not available from the tiled kernel in backpointer mode");
     const bool timed = flags & TORBI_B200_TIME_KERNELS;
     g_timing.valid = false;
     if (timed) {
@@ -280,43 +355,52 @@ int decode_device(const float *observation, const int32_t *batch_frames,
         if (e != cudaSuccess) return fail_cuda(e, "timing events");
     }
 
-    Choice choice = kGeneric;
-    rc = choose_kernel(a, batch_frames, order, flags, &choice);
-    if (rc) return rc;
+    const Choice choice = plan.choice;
     const bool tiled = choice != kGeneric;               // kernels that honour frames_ready
-    if (streamed) *streamed = tiled;
-    g_last_kernel = kernel_name(a, choice, flags);
-    bool history = false;
+    if (opt.streamed) *opt.streamed = tiled;
+    g_last_kernel = kernel_name(plan.tile_rows, choice, flags);
     if (choice == kGeneric) {
-        if (frames_ready)
+        if (opt.frames_ready)
             return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "internal: generic kernel cannot stream");
         e = launch_forward_generic(a, stream);
     } else if (choice == kWide) {
         e = launch_forward_wide(a, stream);
     } else if (choice == kSplit) {
-        history = true;
         e = launch_forward_split(a, stream);
-    } else if (!std::strcmp(g_last_kernel, "forward_tiled_ws")) {
-        e = launch_forward_tiled_ws(a, stream);
-    } else if (workspace_has_history(flags)) {
+    } else if (choice == kCluster) {
+        e = launch_forward_cluster(a, stream);
+    } else if (plan.history) {
         // score-history mode (default): pure max-plus forward, argmax recomputed along the path
-        history = true;
         e = launch_forward_tiled_hist(a, stream);
     } else {
         e = launch_forward_tiled(a, stream);
     }
     if (e != cudaSuccess) return fail_cuda(e, g_last_kernel);
+    int launches = tiled ? (choice == kTiled && (flags & TORBI_B200_BANDED) ? 3 : 2) : 1;   // (pad_transition + [analyze_band] +) forward
+    if (opt.checkpoints && plan.history) {
+        // the score history holds every P_t already: gather the requested rows
+        e = launch_gather_checkpoints(a, stream);
+        if (e != cudaSuccess) return fail_cuda(e, "gather_checkpoints");
+        ++launches;
+    }
     if (timed) cudaEventRecord(g_timing.ev[1], stream);
+    const bool history = plan.history;
+    int backtrace_launches = 1;
     g_last_backtrace = history ? "backtrace_recompute" : "backtrace";
-    e = history ? launch_backtrace_recompute(ws, indices, B, T, S, stream)
-                : launch_backtrace(ws, indices, B, T, S, stream);
+    if (history) {
+        e = launch_backtrace_recompute(ws, indices, B, T, S, stream);
+    } else if (plan.max_frames >= kWindowedBacktraceMinFrames) {
+        g_last_backtrace = "backtrace_blocked";
+        e = launch_backtrace_blocked(ws, indices, B, T, S, plan.max_frames, &backtrace_launches, stream);
+    } else {
+        e = launch_backtrace(ws, indices, B, T, S, stream);
+    }
     if (e != cudaSuccess) return fail_cuda(e, g_last_backtrace);
     if (timed) {
         cudaEventRecord(g_timing.ev[2], stream);
         g_timing.valid = true;
     }
-    // kernels enqueued: (pad_transition + [analyze_band] +) forward + backtrace
-    g_launches += tiled ? (choice == kTiled && (flags & TORBI_B200_BANDED) ? 4 : 3) : 2;
+    g_launches += launches + backtrace_launches;
     return TORBI_B200_OK;
 }
 
@@ -324,34 +408,53 @@ int decode_device(const float *observation, const int32_t *batch_frames,
 
 extern "C" {
 
-int torbi_b200_decode(const float *observation, const int32_t *batch_frames,
+int torbi_b200_decode(const void *observation, const int32_t *batch_frames,
                       const float *transition, const float *initial, int64_t B, int64_t T,
                       int64_t S, uint32_t flags, int32_t *indices, float *posterior,
                       void *workspace, size_t workspace_bytes, void *stream) {
     return guarded([&] {
         return decode_device(observation, batch_frames, transition, initial, B, T, S, flags, indices,
-                             posterior, workspace, workspace_bytes, stream, nullptr, nullptr);
+                             posterior, workspace, workspace_bytes, stream, DecodeOptions{});
     });
+}
+
+int torbi_b200_decode_checkpointed(const void *observation, const int32_t *batch_frames,
+                                   const float *transition, const float *initial, int64_t B, int64_t T,
+                                   int64_t S, uint32_t flags, int32_t *indices, float *posterior,
+                                   void *workspace, size_t workspace_bytes, void *stream,
+                                   float *checkpoints, int64_t checkpoint_every) {
+    return guarded([&] {
+        if (!checkpoints) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+        DecodeOptions opt;
+        opt.checkpoints = checkpoints;
+        opt.checkpoint_every = checkpoint_every;
+        return decode_device(observation, batch_frames, transition, initial, B, T, S, flags, indices,
+                             posterior, workspace, workspace_bytes, stream, opt);
+    });
+}
+
+size_t torbi_b200_workspace_bytes_planned(const int32_t *batch_frames, int64_t B, int64_t T, int64_t S,
+                                          uint32_t flags, int sm_count) {
+    g_error[0] = 0;
+    if (sm_count < 1) return 0;
+    try {
+        Plan plan;
+        if (make_plan(batch_frames, B, T, S, flags, sm_count, &plan) != TORBI_B200_OK) return 0;
+        return plan.workspace_bytes;
+    } catch (...) {
+        fail(TORBI_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
+        return 0;
+    }
 }
 
 const char *torbi_b200_plan(const int32_t *batch_frames, int64_t B, int64_t T, int64_t S,
                             uint32_t flags, int sm_count) {
     g_error[0] = 0;
-    if (validate_shape(B, T, S) != TORBI_B200_OK || !batch_frames || sm_count < 1) return nullptr;
+    if (sm_count < 1) return nullptr;
     try {
-    std::vector<int32_t> order(pad_batch(B), -1);
-    std::iota(order.begin(), order.begin() + B, 0);
-    std::stable_sort(order.begin(), order.begin() + B,
-                     [&](int32_t x, int32_t y) { return batch_frames[x] > batch_frames[y]; });
-    ForwardArgs a{};
-    a.B = B; a.T = T; a.S = S;
-    a.flags = flags;
-    a.sm_count = sm_count;
-    a.ws = carve_workspace(reinterpret_cast<void *>(uintptr_t(256)), B, T, S, flags);   // layout only, never dereferenced
-    a.observation = reinterpret_cast<const float *>(uintptr_t(256));
-    Choice choice = kGeneric;
-    if (choose_kernel(a, batch_frames, order, flags, &choice) != TORBI_B200_OK) return nullptr;
-    return kernel_name(a, choice, flags);
+        Plan plan;
+        if (make_plan(batch_frames, B, T, S, flags, sm_count, &plan) != TORBI_B200_OK) return nullptr;
+        return kernel_name(plan.tile_rows, plan.choice, plan.flags);
     } catch (...) {
         fail(TORBI_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
         return nullptr;
@@ -413,7 +516,7 @@ struct DeviceGuard {
 };
 
 // Decode `count` items (given by index into the caller's batch) on one device.
-int decode_items_on_device(const float *observation, const int32_t *batch_frames,
+int decode_items_on_device(const void *observation_, const int32_t *batch_frames,
                            const float *transition, const float *initial,
                            const int32_t *items, int64_t count, int64_t T, int64_t S,
                            uint32_t flags, int32_t *indices, float *posterior, int device) {
@@ -424,12 +527,24 @@ int decode_items_on_device(const float *observation, const int32_t *batch_frames
     Arena *arena = arena_for(device);
     std::lock_guard<std::mutex> lock(arena->busy);
 
-    const size_t obs_bytes = align_up(sizeof(float) * count * T * S, 256);
+    // everything that can be rejected is rejected before a single copy is enqueued: lengths, flags,
+    // the kernel choice (a forced kernel that does not support the shape) and the workspace size
+    std::vector<int32_t> frames(count);
+    for (int64_t i = 0; i < count; ++i) frames[i] = batch_frames[items[i]];
+    Plan plan;
+    rc = make_plan(frames.data(), count, T, S, flags, info.sm_count, &plan);
+    if (rc) return rc;
+
+    // fp16 / bf16 observations stay 2 bytes per element on the wire and in HBM; the kernels upcast
+    // in their observation load (exact: every half value is an fp32 value)
+    const size_t elem = (flags & (TORBI_B200_OBS_F16 | TORBI_B200_OBS_BF16)) ? 2 : 4;
+    const char *observation = static_cast<const char *>(observation_);
+    const size_t obs_bytes = align_up(elem * count * T * S, 256);
     const size_t tr_bytes = align_up(sizeof(float) * S * S, 256);
     const size_t init_bytes = align_up(sizeof(float) * S, 256);
     const size_t idx_bytes = align_up(sizeof(int32_t) * count * T, 256);
     const size_t post_bytes = posterior ? align_up(sizeof(float) * count * S, 256) : 0;
-    const size_t ws_bytes = carve_workspace(nullptr, count, T, S, flags).bytes;
+    const size_t ws_bytes = plan.workspace_bytes;
     const size_t total = obs_bytes + tr_bytes + init_bytes + idx_bytes + post_bytes + ws_bytes + 256;
 
     cudaError_t e;
@@ -455,7 +570,7 @@ int decode_items_on_device(const float *observation, const int32_t *batch_frames
         arena->bytes = total;
     }
     char *p = static_cast<char *>(arena->base);
-    float *d_obs = reinterpret_cast<float *>(p); p += obs_bytes;
+    char *d_obs = p; p += obs_bytes;
     float *d_tr = reinterpret_cast<float *>(p); p += tr_bytes;
     float *d_init = reinterpret_cast<float *>(p); p += init_bytes;
     int32_t *d_idx = reinterpret_cast<int32_t *>(p); p += idx_bytes;
@@ -467,19 +582,28 @@ int decode_items_on_device(const float *observation, const int32_t *batch_frames
     e = cudaMemcpyAsync(d_tr, transition, sizeof(float) * S * S, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(d_init, initial, sizeof(float) * S, cudaMemcpyHostToDevice, stream);
-    std::vector<int32_t> frames(count);
-    for (int64_t i = 0; i < count; ++i) frames[i] = batch_frames[items[i]];
+    // once anything is in flight, every exit waits for both streams: the next call on this arena
+    // must not overlap leftover copies, and the caller may free its (pinned) buffers on return
+    struct Drain {
+        Arena *arena;
+        bool armed = true;
+        ~Drain() {
+            if (!armed) return;
+            cudaStreamSynchronize(arena->stream);
+            cudaStreamSynchronize(arena->copy_stream);
+            cudaGetLastError();
+        }
+    } drain{arena};
 
     // Large pinned batches are streamed in along T on a second stream while the
     // forward kernel already runs: step t only needs frame t (the kernel polls
     // `d_ready`).  Small, pageable or generic-kernel batches are copied up front.
-    const size_t row_bytes = sizeof(float) * T * S;
+    const size_t row_bytes = elem * T * S;
     cudaPointerAttributes attr{};
     const bool pinned = cudaPointerGetAttributes(&attr, observation) == cudaSuccess &&
                         attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    const bool can_tile = padded_dests(S) / kTileDests <= info.sm_count && !(flags & TORBI_B200_FORCE_GENERIC);
-    const bool stream_in = pinned && can_tile && T >= 64 && row_bytes < (size_t(1) << 31) &&
+    const bool stream_in = pinned && plan.choice != kGeneric && T >= 64 && row_bytes < (size_t(1) << 31) &&
                            (size_t)count * row_bytes >= (size_t(64) << 20);
     const int chunks = stream_in ? (int)std::min<int64_t>(kMaxChunks, std::max<int64_t>(2, T / 16)) : 1;
     // Chunk boundaries along T.  The forward kernel trails the copy by one chunk (step t needs the whole
@@ -507,12 +631,12 @@ int decode_items_on_device(const float *observation, const int32_t *batch_frames
         for (int64_t i = 0; i < count && e == cudaSuccess;) {
             int64_t run = 1;
             while (i + run < count && items[i + run] == items[i] + run) ++run;
-            const float *src = observation + (int64_t)items[i] * T * S + t0 * S;
-            float *dst = d_obs + i * T * S + t0 * S;
+            const char *src = observation + ((int64_t)items[i] * T * S + t0 * S) * elem;
+            char *dst = d_obs + (i * T * S + t0 * S) * elem;
             if (chunks == 1)
                 e = cudaMemcpyAsync(dst, src, row_bytes * run, cudaMemcpyHostToDevice, stream);
             else
-                e = cudaMemcpy2DAsync(dst, row_bytes, src, row_bytes, sizeof(float) * (t1 - t0) * S,
+                e = cudaMemcpy2DAsync(dst, row_bytes, src, row_bytes, elem * (t1 - t0) * S,
                                       run, cudaMemcpyHostToDevice, arena->copy_stream);
             i += run;
         }
@@ -525,8 +649,12 @@ int decode_items_on_device(const float *observation, const int32_t *batch_frames
     if (e != cudaSuccess) return fail_cuda(e, "host->device copy");
 
     bool streamed = false;
+    DecodeOptions opt;
+    opt.frames_ready = stream_in ? d_ready : nullptr;
+    opt.streamed = &streamed;
+    opt.plan = &plan;
     rc = decode_device(d_obs, frames.data(), d_tr, d_init, count, T, S, flags, d_idx, d_post, d_ws,
-                       ws_bytes, stream, stream_in ? d_ready : nullptr, &streamed);
+                       ws_bytes, stream, opt);
     if (rc) return rc;
 
     for (int64_t i = 0; i < count && e == cudaSuccess;) {
@@ -542,10 +670,11 @@ int decode_items_on_device(const float *observation, const int32_t *batch_frames
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     if (e == cudaSuccess && stream_in) e = cudaStreamSynchronize(arena->copy_stream);
     if (e != cudaSuccess) return fail_cuda(e, "device->host copy / synchronize");
+    drain.armed = false;
     return TORBI_B200_OK;
 }
 
-int validate_host_args(const float *observation, const int32_t *batch_frames,
+int validate_host_args(const void *observation, const int32_t *batch_frames,
                        const float *transition, const float *initial, int64_t B, int64_t T,
                        int64_t S, const int32_t *indices) {
     int rc = validate_shape(B, T, S);
@@ -563,7 +692,7 @@ int validate_host_args(const float *observation, const int32_t *batch_frames,
 
 extern "C" {
 
-int torbi_b200_decode_host(const float *observation, const int32_t *batch_frames,
+int torbi_b200_decode_host(const void *observation, const int32_t *batch_frames,
                            const float *transition, const float *initial, int64_t B, int64_t T,
                            int64_t S, uint32_t flags, int32_t *indices, float *posterior,
                            int device) {
@@ -578,7 +707,7 @@ int torbi_b200_decode_host(const float *observation, const int32_t *batch_frames
     });
 }
 
-int torbi_b200_decode_host_multi(const float *observation, const int32_t *batch_frames,
+int torbi_b200_decode_host_multi(const void *observation, const int32_t *batch_frames,
                                  const float *transition, const float *initial, int64_t B,
                                  int64_t T, int64_t S, uint32_t flags, int32_t *indices,
                                  float *posterior, const int *devices, int n_devices) {

@@ -5,6 +5,8 @@
 //   idx = final_state[b]; for t = frames_b-1 .. 1: idx = bp[b,t,idx]; indices[b,t-1] = idx
 // One CTA per sequence: thread 0 chases the dependent uint16 loads while the
 // other threads write the tail.  Per-item batch_frames, 64-bit offsets.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -31,6 +33,164 @@ backtrace_kernel(const uint16_t *__restrict__ backptr, const int32_t *__restrict
         for (int64_t t = frames - 1 + (threadIdx.x - 1); t < T; t += kBacktraceThreads - 1)
             out[t] = last;
     }
+}
+
+// ---------------------------------------------------------------------------
+// Blocked backtrace for long sequences with stored backpointers (config 5: 4096 states x 10^6
+// frames).  backtrace_kernel above is one thread chasing frames_b dependent 2-byte loads, each an
+// L2 / HBM miss (~0.7 us): 0.7 s for 10^6 frames.  The chain idx_{t-1} = bp[t][idx_t] is a
+// composition of maps on {0..S-1}, so it is cut into blocks of K frames:
+//   1. compose (grid: blocks x sequences, all SMs): f_m(s) = state at time lo_m - 1 when the path is
+//      in state s at time hi_m, for ALL s at once -- every thread carries a few states through the
+//      block's K rows (the rows are prefetched into L2 ahead; gathers within a row hit L1 / L2);
+//   2. link (one thread per sequence): the state at every block boundary, entry_{m+1} = f_m(entry_m),
+//      a chain of only frames / K lookups;
+//   3. chase (grid: blocks x sequences): every block follows its own K backpointers from its known
+//      entry state -- the same dependent loads as before, but all blocks at once.
+// Same loads, same table: the indices are those of the plain chase, bit for bit.  The maps live in
+// the forward-score buffers of the workspace, which are dead once the forward kernel has finished.
+// ---------------------------------------------------------------------------
+namespace {
+
+constexpr int kComposeThreads = 1024;
+constexpr int kComposeStatesPerThread = 64;         // S <= 65535
+constexpr int kPrefetchRows = 12;
+
+__device__ __forceinline__ void prefetch_l2_line(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+struct BlockedGeometry {
+    int64_t K;            // frames per block
+    int64_t max_blocks;   // blocks of the longest sequence
+};
+
+// block m of a sequence with `frames` frames covers t in [lo, hi], hi = frames - 1 - m K, lo = max(1, hi - K + 1)
+template <int kPerThread>       // states carried per thread: S <= kPerThread * kComposeThreads
+__global__ void __launch_bounds__(kComposeThreads)
+backtrace_compose_kernel(const uint16_t *__restrict__ backptr, const int32_t *__restrict__ frames_d,
+                         uint16_t *__restrict__ maps, int64_t T, int S, int64_t K, int64_t max_blocks) {
+    const int64_t b = blockIdx.y, m = blockIdx.x;
+    const int64_t hi = (int64_t)frames_d[b] - 1 - m * K;
+    if (hi < 1) return;
+    const int64_t lo = max((int64_t)1, hi - K + 1);
+    const uint16_t *bp = backptr + b * T * S;
+    int cur[kPerThread];
+#pragma unroll
+    for (int i = 0; i < kPerThread; ++i) cur[i] = min(threadIdx.x + i * kComposeThreads, S - 1);
+    const int64_t row_bytes = (int64_t)S * 2;
+    for (int64_t t = hi; t >= lo; --t) {
+        // rows are contiguous: pull the one kPrefetchRows ahead into L2 (one 128-byte line per thread)
+        const int64_t tp = t - kPrefetchRows;
+        if (tp >= lo)
+            for (int64_t off = (int64_t)threadIdx.x * 128; off < row_bytes; off += (int64_t)kComposeThreads * 128)
+                prefetch_l2_line(reinterpret_cast<const char *>(bp + tp * S) + off);
+        const uint16_t *row = bp + t * S;
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i) cur[i] = row[cur[i]];        // (slots past S - 1 repeat state S - 1)
+    }
+    uint16_t *out = maps + (b * max_blocks + m) * S;
+#pragma unroll
+    for (int i = 0; i < kPerThread; ++i)
+        if (threadIdx.x + i * kComposeThreads < S) out[threadIdx.x + i * kComposeThreads] = (uint16_t)cur[i];
+}
+
+__global__ void backtrace_link_kernel(const uint16_t *__restrict__ maps, const int32_t *__restrict__ frames_d,
+                                      const int32_t *__restrict__ final_state, int32_t *__restrict__ entry,
+                                      int64_t B, int S, int64_t K, int64_t max_blocks) {
+    const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int idx = final_state[b];
+    const int64_t frames = frames_d[b];
+    for (int64_t m = 0; m < max_blocks; ++m) {
+        entry[b * max_blocks + m] = idx;                      // state at time hi_m
+        if (frames - 1 - m * K < 1) break;
+        idx = maps[(b * max_blocks + m) * S + idx];
+    }
+}
+
+__global__ void __launch_bounds__(kBacktraceThreads)
+backtrace_chase_kernel(const uint16_t *__restrict__ backptr, const int32_t *__restrict__ frames_d,
+                       const int32_t *__restrict__ final_state, const int32_t *__restrict__ entry,
+                       int32_t *__restrict__ indices, int64_t T, int64_t S, int64_t K, int64_t max_blocks) {
+    const int64_t b = blockIdx.y, m = blockIdx.x;
+    const int64_t frames = frames_d[b];
+    int32_t *out = indices + b * T;
+    if (m == 0 && threadIdx.x > 0) {
+        const int last = final_state[b];                      // viterbi.cpp:219-221
+        for (int64_t t = frames - 1 + (threadIdx.x - 1); t < T; t += kBacktraceThreads - 1) out[t] = last;
+        return;
+    }
+    const int64_t hi = frames - 1 - m * K;
+    if (hi < 1 || threadIdx.x != 0) return;
+    const int64_t lo = max((int64_t)1, hi - K + 1);
+    const uint16_t *bp = backptr + b * T * S;
+    int idx = entry[b * max_blocks + m];
+    for (int64_t t = hi; t >= lo; --t) {
+        idx = bp[t * S + idx];
+        out[t - 1] = idx;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_backtrace_blocked(const Workspace &ws, int32_t *indices, int64_t B, int64_t T, int64_t S,
+                                     int64_t max_frames, int *launches, cudaStream_t stream) {
+    // maps + entry states go where the rotating forward scores were (score[0] .. transition_pad)
+    char *region = reinterpret_cast<char *>(ws.score[0]);
+    const size_t capacity = reinterpret_cast<char *>(ws.transition_pad) - region - 256;
+    const size_t per_block = (size_t)B * ((size_t)S * sizeof(uint16_t) + sizeof(int32_t));   // one map + one entry per sequence
+    int64_t max_blocks = (int64_t)std::min<size_t>(capacity / per_block, 65535);
+    max_blocks = std::min<int64_t>(max_blocks, (max_frames - 1 + 255) / 256);               // blocks of >= 256 frames
+    if (max_blocks < 2 || S > (int64_t)kComposeThreads * kComposeStatesPerThread) {
+        if (launches) *launches = 1;
+        return launch_backtrace(ws, indices, B, T, S, stream);
+    }
+    const int64_t K = (max_frames - 1 + max_blocks - 1) / max_blocks;
+    max_blocks = (max_frames - 1 + K - 1) / K;
+    uint16_t *maps = reinterpret_cast<uint16_t *>(region);
+    int32_t *entry = reinterpret_cast<int32_t *>(region + align_up((size_t)B * max_blocks * S * sizeof(uint16_t), 256));
+    const dim3 grid((unsigned)max_blocks, (unsigned)B);
+    if (S <= 2 * kComposeThreads)
+        backtrace_compose_kernel<2><<<grid, kComposeThreads, 0, stream>>>(ws.backptr, ws.frames, maps, T, (int)S, K, max_blocks);
+    else if (S <= 4 * kComposeThreads)
+        backtrace_compose_kernel<4><<<grid, kComposeThreads, 0, stream>>>(ws.backptr, ws.frames, maps, T, (int)S, K, max_blocks);
+    else if (S <= 16 * kComposeThreads)
+        backtrace_compose_kernel<16><<<grid, kComposeThreads, 0, stream>>>(ws.backptr, ws.frames, maps, T, (int)S, K, max_blocks);
+    else
+        backtrace_compose_kernel<kComposeStatesPerThread><<<grid, kComposeThreads, 0, stream>>>(ws.backptr, ws.frames, maps, T, (int)S, K, max_blocks);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    backtrace_link_kernel<<<(unsigned)((B + 127) / 128), 128, 0, stream>>>(maps, ws.frames, ws.final_state, entry, B,
+                                                                          (int)S, K, max_blocks);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    backtrace_chase_kernel<<<dim3((unsigned)max_blocks, (unsigned)B), kBacktraceThreads, 0, stream>>>(
+        ws.backptr, ws.frames, ws.final_state, entry, indices, T, S, K, max_blocks);
+    if (launches) *launches = 3;
+    return cudaGetLastError();
+}
+
+// torbi_b200_decode_checkpointed after a score-history kernel: the history already holds every P_t
+namespace {
+__global__ void gather_checkpoints_kernel(const float *__restrict__ history, const int32_t *__restrict__ frames_d,
+                                          float *__restrict__ checkpoints, int64_t B, int64_t T, int64_t S,
+                                          int64_t every, int64_t rows) {
+    const int64_t total = B * rows * S;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = i % S, k = (i / S) % rows, b = i / (S * rows);
+        const int64_t t = (k + 1) * every;
+        if (t < frames_d[b]) checkpoints[i] = history[(b * T + t) * S + s];
+    }
+}
+}  // namespace
+
+cudaError_t launch_gather_checkpoints(const ForwardArgs &a, cudaStream_t stream) {
+    const int64_t rows = (a.T - 1) / a.checkpoint_every;
+    if (rows < 1) return cudaSuccess;
+    gather_checkpoints_kernel<<<a.sm_count * 4, 256, 0, stream>>>(
+        reinterpret_cast<const float *>(a.ws.backptr), a.ws.frames, a.checkpoints, a.B, a.T, a.S, a.checkpoint_every, rows);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------

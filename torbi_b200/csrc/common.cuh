@@ -4,6 +4,7 @@
 #include <cfloat>
 #include <cstdint>
 #include <cstdio>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "../../include/torbi_b200.h"
@@ -48,6 +49,56 @@ __device__ __forceinline__ float convert_observation_rt(float x, uint32_t flags)
     return x;
 }
 
+// ---------------------------------------------------------------------------
+// Observation loads.  `observation` is fp32, or fp16 / bf16 with TORBI_B200_OBS_F16 / _BF16 (dtype 1 / 2):
+// the reference casts whatever dtype it is given to fp32 on the host (core.py:191); here the 2-byte
+// elements are upcast at the load -- exact, every half / bfloat16 value is an fp32 value.
+// All loads are L2-coherent (.cg): the host entry may still be copying later frames of the same buffer
+// while the kernel runs, and a non-coherent (.nc) or L1-cached load could return a stale sector that
+// straddles a frame boundary.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float half_bits_to_float(unsigned short raw, int dtype) {
+    return dtype == 1 ? __half2float(__ushort_as_half(raw)) : __uint_as_float((unsigned)raw << 16);
+}
+__device__ __forceinline__ float load_observation(const void *base, int64_t index, int dtype) {
+    if (dtype == 0) return __ldcg(static_cast<const float *>(base) + index);
+    return half_bits_to_float(__ldcg(static_cast<const unsigned short *>(base) + index), dtype);
+}
+
+// Emission tile of one timestep without cp.async (2-byte observations, S % 4 != 0 or an unaligned
+// base): tile[r][c] = raw observation of slot r, state j0 + c, for live slots; plain shared-memory
+// stores, the caller synchronises before the tile is consumed.
+template <int TM, int TN, int kThreads>
+__device__ __forceinline__ void load_emission_tile_plain(float *tile, const void *observation, int dtype,
+                                                         const int *slot_item, const int *slot_frames,
+                                                         int64_t T, int S, int t, int j0) {
+    const bool half4 = dtype != 0 && (S % 4) == 0 && (reinterpret_cast<uintptr_t>(observation) & 7) == 0;
+    if (half4) {
+        // four 2-byte elements per 8-byte load
+        for (int idx = threadIdx.x; idx < TM * (TN / 4); idx += kThreads) {
+            const int r = idx / (TN / 4), c4 = idx % (TN / 4);
+            const int item = slot_item[r];
+            if (item >= 0 && t < slot_frames[r] && j0 + c4 * 4 < S) {
+                const uint2 raw = __ldcg(reinterpret_cast<const uint2 *>(
+                    static_cast<const unsigned short *>(observation) + ((int64_t)item * T + t) * S + j0 + c4 * 4));
+                float4 v;
+                v.x = half_bits_to_float((unsigned short)(raw.x & 0xffffu), dtype);
+                v.y = half_bits_to_float((unsigned short)(raw.x >> 16), dtype);
+                v.z = half_bits_to_float((unsigned short)(raw.y & 0xffffu), dtype);
+                v.w = half_bits_to_float((unsigned short)(raw.y >> 16), dtype);
+                *reinterpret_cast<float4 *>(tile + r * TN + c4 * 4) = v;
+            }
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < TM * TN; idx += kThreads) {
+            const int r = idx / TN, c = idx % TN;
+            const int item = slot_item[r];
+            if (item >= 0 && t < slot_frames[r] && j0 + c < S)
+                tile[idx] = load_observation(observation, ((int64_t)item * T + t) * S + j0 + c, dtype);
+        }
+    }
+}
+
 // (value, index) ordering of the reference's strict-`>` ascending scan
 // (/root/reference/torbi/csrc/viterbi.cpp:94-101): larger value wins, equal
 // values keep the LOWER source index.
@@ -90,7 +141,11 @@ inline int64_t pad_batch(int64_t B) { return (B + 127) / 128 * 128; }
 // `history`: size the backpointer region for fp32 scores (unless TORBI_B200_BACKPOINTERS is set)
 inline bool workspace_has_history(uint32_t flags) { return !(flags & TORBI_B200_BACKPOINTERS); }
 
-inline Workspace carve_workspace(void *base, int64_t B, int64_t T, int64_t S, uint32_t flags) {
+// `history` = the trailing region holds fp32 forward scores (4 bytes per (b,t,s): tiled kernel in
+// score-history mode, split / cluster kernels) rather than uint16 backpointers (2 bytes: wide and generic
+// kernels, tiled kernel in backpointer mode).  Everything before that region has the same layout
+// either way, so the region can be sized after the kernel has been chosen.
+inline Workspace carve_workspace(void *base, int64_t B, int64_t T, int64_t S, bool history) {
     Workspace w{};
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -110,7 +165,7 @@ inline Workspace carve_workspace(void *base, int64_t B, int64_t T, int64_t S, ui
     w.block_max = static_cast<float *>(take(sizeof(float) * 3 * Bp * (Sp / 16)));
     w.transition_pad = static_cast<float *>(take(sizeof(float) * padded_dests(S) * Sp));
     w.backptr = static_cast<uint16_t *>(
-        take((workspace_has_history(flags) ? sizeof(float) : sizeof(uint16_t)) * B * T * S));
+        take((history ? sizeof(float) : sizeof(uint16_t)) * B * T * S));
     w.bytes = off;
     return w;
 }

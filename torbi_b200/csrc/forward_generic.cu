@@ -20,7 +20,8 @@ constexpr int kGenericThreads = 512;
 
 template <uint32_t kFlags>
 __global__ void __launch_bounds__(kGenericThreads)
-forward_generic_kernel(const float *__restrict__ observation,
+forward_generic_kernel(const float *__restrict__ observation, int obs_dtype,
+                       float *__restrict__ checkpoints, int64_t checkpoint_every,
                        const int32_t *__restrict__ frames_d,
                        const float *__restrict__ transition,
                        const float *__restrict__ initial, float *score0, float *score1,
@@ -33,7 +34,8 @@ forward_generic_kernel(const float *__restrict__ observation,
 
     const int64_t b = blockIdx.x;
     const int frames = frames_d[b];
-    const float *obs = observation + b * T * S;
+    const int64_t obs0 = b * T * S;                     // element offset of this sequence
+    const int64_t ck_rows = checkpoints ? (T - 1) / checkpoint_every : 0;
     uint16_t *bp = backptr + b * T * S;
     float *cur = scores_in_smem ? smem_scores : score0 + b * score_stride;
     float *nxt = scores_in_smem ? smem_scores + S : score1 + b * score_stride;
@@ -43,17 +45,19 @@ forward_generic_kernel(const float *__restrict__ observation,
     const int nwarps = blockDim.x / kWarp;
 
     for (int i = threadIdx.x; i < S; i += blockDim.x)
-        cur[i] = convert_observation<kFlags>(obs[i]) + initial[i];
+        cur[i] = convert_observation<kFlags>(load_observation(observation, obs0 + i, obs_dtype)) + initial[i];
     __syncthreads();
 
     const bool vec4 = (S % 4) == 0;
     for (int t = 1; t < frames; ++t) {
-        const float *obs_t = obs + (int64_t)t * S;
+        const int64_t obs_t = obs0 + (int64_t)t * S;
+        float *ck = (checkpoints && t % checkpoint_every == 0)
+            ? checkpoints + (b * ck_rows + (t / checkpoint_every - 1)) * S : nullptr;
         uint16_t *bp_t = bp + (int64_t)t * S;
         for (int j = warp; j < S; j += nwarps) {
             const float *row = transition + (int64_t)j * S;
             float emit = 0.f;
-            if (lane == 0) emit = convert_observation<kFlags>(obs_t[j]);
+            if (lane == 0) emit = convert_observation<kFlags>(load_observation(observation, obs_t + j, obs_dtype));
             float best = -INFINITY;
             int arg = 0x7fffffff;
             bool any = false;
@@ -87,6 +91,7 @@ forward_generic_kernel(const float *__restrict__ observation,
             if (lane == 0) {
                 bp_t[j] = static_cast<uint16_t>(arg);
                 nxt[j] = emit + best;
+                if (ck) ck[j] = emit + best;
             }
         }
         float *tmp = cur; cur = nxt; nxt = tmp;
@@ -129,7 +134,7 @@ static cudaError_t launch_generic_t(const ForwardArgs &a, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
     }
     kernel<<<(unsigned)a.B, kGenericThreads, smem, stream>>>(
-        a.observation, a.ws.frames, a.transition, a.initial, a.ws.score[0], a.ws.score[1],
+        a.observation, a.obs_dtype, a.checkpoints, a.checkpoint_every, a.ws.frames, a.transition, a.initial, a.ws.score[0], a.ws.score[1],
         a.ws.backptr, a.posterior, a.ws.final_state, a.T, (int)a.S, padded_sources(a.S), in_smem);
     return cudaGetLastError();
 }

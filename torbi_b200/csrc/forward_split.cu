@@ -137,7 +137,8 @@ __device__ __forceinline__ void group_wait(const unsigned *counter, unsigned tar
 #endif
 
 struct SplitParams {
-    const float *observation;   // (B,T,S)
+    const float *observation;   // (B,T,S); 2-byte elements when obs_dtype != 0
+    int obs_dtype;              // 0 fp32, 1 fp16, 2 bf16
     const float *transition;    // padded copy (SJ, LDP), -inf outside (S,S)
     const float *initial;       // (S,)
     const int32_t *frames;      // (B,)
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_split_kernel(const SplitP
     const int lane_b = lane / LANES_J, lane_j = lane % LANES_J;      // rows lane_b + 4 i, cols lane_j + 8 c
     const int S = p.S, LDP = p.LDP;
     const int nstages = (LDP + KS - 1) / KS;           // (resident shape: the last stage may be half empty)
-    const bool obs_vec = (S % 4) == 0 && (reinterpret_cast<uintptr_t>(p.observation) & 15) == 0;
+    const bool obs_vec = p.obs_dtype == 0 && (S % 4) == 0 && (reinterpret_cast<uintptr_t>(p.observation) & 15) == 0;
     const bool hist_vec = (S % 4) == 0;
     const int ld_c4 = tid % (KS / 4), ld_r0 = tid / (KS / 4);
     const int ld_smem = ld_r0 * LDS_ + ld_c4 * 4;
@@ -278,10 +279,10 @@ __global__ void __launch_bounds__(kThreads, 1) forward_split_kernel(const SplitP
                 float *dst0 = p.score0 + (row0 + r) * LDP;
                 float *dst1 = dst0 + p.score_stride;
                 float *dst2 = dst1 + p.score_stride;
-                const float *obs = p.observation + (int64_t)max(item, 0) * p.T * S;
+                const int64_t obs0 = (int64_t)max(item, 0) * p.T * S;
                 for (int c = j0 + lane; c < c_end; c += kWarp) {
                     if (item >= 0 && c < S) {
-                        const float v = convert_observation<kFlags>(obs[c]) + p.initial[c];
+                        const float v = convert_observation<kFlags>(load_observation(p.observation, obs0 + c, p.obs_dtype)) + p.initial[c];
                         dst0[c] = v;
                         p.history[(int64_t)item * p.T * S + c] = v;
                     } else {
@@ -309,12 +310,8 @@ __global__ void __launch_bounds__(kThreads, 1) forward_split_kernel(const SplitP
                         cp_async16(tile + r * TN + c4 * 4, p.observation + ((int64_t)item * p.T + t) * S + j0 + c4 * 4);
                 }
             } else {
-                for (int idx = tid; idx < TM * TN; idx += kThreads) {
-                    const int r = idx / TN, c = idx % TN;
-                    const int item = slot_item[r];
-                    if (item >= 0 && t < slot_frames[r] && j0 + c < S)
-                        tile[idx] = __ldg(p.observation + ((int64_t)item * p.T + t) * S + j0 + c);
-                }
+                load_emission_tile_plain<TM, TN, kThreads>(tile, p.observation, p.obs_dtype, slot_item, slot_frames,
+                                                           p.T, S, t, j0);
             }
             for (int s = 0; s < ahead; ++s)
                 load_stage_A<Shape>(ring + ((slot + s) % NSTAGE) * kStageFloats + ld_smem, ld_A + s * KS, ld_stride10);
@@ -400,23 +397,23 @@ __global__ void __launch_bounds__(kThreads, 1) forward_split_kernel(const SplitP
                     const unsigned aslot = (slot + s) % NSTAGE;
                     load_stage_P<Shape>(ring + aslot * kStageFloats + ld_smem, ld_P + s * KS, ld_stride10, ld_r0,
                                         KS == kStageSources || s * KS + ld_c4 * 4 < LDP);
-                    cp_async_arrive(full_bar + aslot);
+                    ring_full_arrive(full_bar + aslot);
                 }
                 for (int s = 0; s < nstages; ++s) {
-                    mbar_wait(full_bar + slot, full_parity);                       // everyone's copies have landed
+                    ring_full_wait(full_bar + slot, full_parity);                       // everyone's copies have landed
                     if (s == 0) { PROF_MARK(0) }
                     // refill the slot the previous stage used with stage s + NSTAGE - 1
                     if (s + NSTAGE - 1 < nstages) {
                         const unsigned rslot = slot == 0 ? NSTAGE - 1 : slot - 1;
                         if (s > 0) {    // (s == 0: its last readers belong to the previous step, behind CTA barriers)
-                            mbar_wait(empty_bar + rslot, (empty_parity >> rslot) & 1u);
+                            ring_empty_wait(empty_bar + rslot, (empty_parity >> rslot) & 1u);
                             empty_parity ^= 1u << rslot;
                         }
                         float *dst = ring + rslot * kStageFloats + ld_smem;
                         load_stage_A<Shape>(dst, ld_A + (s + NSTAGE - 1) * KS, ld_stride10);
                         load_stage_P<Shape>(dst, ld_P + (s + NSTAGE - 1) * KS, ld_stride10, ld_r0,
                                             KS == kStageSources || (s + NSTAGE - 1) * KS + ld_c4 * 4 < LDP);
-                        cp_async_arrive(full_bar + rslot);
+                        ring_full_arrive(full_bar + rslot);
                     }
                     const float *Ps = ring + slot * kStageFloats + lane_b * LDS_;
                     const float *As = Shape::kResident ? A_res + lane_j * LDA + s * KS
@@ -447,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_split_kernel(const SplitP
                     // signalled only when a refill (during the next stage) is going to wait for it
                     if (s + NSTAGE < nstages) {
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(empty_bar + slot);
+                        if (lane == 0) ring_empty_arrive(empty_bar + slot);
                     }
                     if (++slot == NSTAGE) { slot = 0; full_parity ^= 1u; }
                 }
@@ -567,6 +564,7 @@ template <typename Shape>
 static cudaError_t launch_split_t(const ForwardArgs &a, cudaStream_t stream) {
     SplitParams p{};
     p.observation = a.observation;
+    p.obs_dtype = a.obs_dtype;
     p.transition = a.ws.transition_pad;
     p.initial = a.initial;
     p.frames = a.ws.frames;

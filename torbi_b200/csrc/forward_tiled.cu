@@ -133,7 +133,8 @@ __device__ __forceinline__ void group_wait(const unsigned *counter, unsigned tar
 }
 
 struct TiledParams {
-    const float *observation;   // (B,T,S)
+    const float *observation;   // (B,T,S); 2-byte elements when obs_dtype != 0
+    int obs_dtype;              // 0 fp32, 1 fp16, 2 bf16
     const float *transition;    // padded copy (SJ, LDP), -inf outside (S,S)
     const float *initial;       // (S,)
     const int32_t *frames;      // (B,)
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
     const int nstages = s_hi - s_lo;
     const int stage_base = s_lo * KS;                             // first source state staged
     const int k_lo = c_lo * KC, k_hi = min(c_hi * KC, S);         // sources covered by the dense loop
-    const bool obs_vec = (S % 4) == 0 && (reinterpret_cast<uintptr_t>(p.observation) & 15) == 0;
+    const bool obs_vec = p.obs_dtype == 0 && (S % 4) == 0 && (reinterpret_cast<uintptr_t>(p.observation) & 15) == 0;
     const bool bp_vec = (S % 8) == 0;
     const bool hist_vec = (S % 4) == 0;
     // loader mapping (see load_stage)
@@ -388,10 +389,10 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                 float *dst0 = p.score0 + (row0 + r) * LDP;
                 float *dst1 = dst0 + p.score_stride;
                 float *dst2 = dst1 + p.score_stride;
-                const float *obs = p.observation + (int64_t)max(item, 0) * p.T * S;
+                const int64_t obs0 = (int64_t)max(item, 0) * p.T * S;
                 for (int c = j0 + lane; c < c_end; c += kWarp) {
                     if (item >= 0 && c < S) {
-                        const float v = convert_observation<kFlags>(obs[c]) + p.initial[c];
+                        const float v = convert_observation<kFlags>(load_observation(p.observation, obs0 + c, p.obs_dtype)) + p.initial[c];
                         dst0[c] = v;
                         if (kHist) p.history[(int64_t)item * p.T * S + c] = v;
                     } else {
@@ -434,12 +435,8 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                                    p.observation + ((int64_t)item * p.T + t) * S + j0 + c4 * 4);
                 }
             } else {
-                for (int idx = tid; idx < TM * TN; idx += kThreads) {
-                    const int r = idx / TN, c = idx % TN;
-                    const int item = slot_item[r];
-                    if (item >= 0 && t < slot_frames[r] && j0 + c < S)
-                        tile[idx] = __ldg(p.observation + ((int64_t)item * p.T + t) * S + j0 + c);
-                }
+                load_emission_tile_plain<TM, TN, kThreads>(tile, p.observation, p.obs_dtype, slot_item, slot_frames,
+                                                           p.T, S, t, j0);
             }
             // (stage_counter already points at the first stage of step t: the previous step is done)
             if (nstages > 0) load_stage_A<TM>(ring + (stage_counter % NSTAGE) * kStageFloats + ld_smem, ld_A, ld_stride10);
@@ -466,11 +463,11 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                 const unsigned slot0 = stage_counter % NSTAGE, slot1 = (stage_counter + 1) % NSTAGE;
                 if (nstages > 0) {
                     load_stage_P<TM>(ring + slot0 * kStageFloats + ld_smem, ld_P, ld_stride10, ld_r0);
-                    cp_async_arrive(full_bar + slot0);
+                    ring_full_arrive(full_bar + slot0);
                 }
                 if (nstages > 1) {
                     load_stage_P<TM>(ring + slot1 * kStageFloats + ld_smem, ld_P + KS, ld_stride10, ld_r0);
-                    cp_async_arrive(full_bar + slot1);
+                    ring_full_arrive(full_bar + slot1);
                 }
             }
 
@@ -565,7 +562,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             for (int s = 0; s < nstages; ++s, ++stage_counter) {
                 const unsigned slot = stage_counter % NSTAGE;
                 // every thread's copies for this stage have landed
-                mbar_wait(full_bar + slot, (stage_counter / NSTAGE) & 1);
+                ring_full_wait(full_bar + slot, (stage_counter / NSTAGE) & 1);
                 if (s == 0) { PROF_MARK(0) }
                 const bool refill = s + 2 < nstages;
                 const unsigned rslot = (stage_counter + 2) % NSTAGE;          // the previous stage's slot
@@ -581,11 +578,11 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                         // warp has (almost surely) released it, so the wait does not couple the warps.
                         // (s == 0: the slot's last readers belong to the previous step, behind CTA barriers)
                         if (s > 0) {
-                            mbar_wait(empty_bar + rslot, (empty_parity >> rslot) & 1u);
+                            ring_empty_wait(empty_bar + rslot, (empty_parity >> rslot) & 1u);
                             empty_parity ^= 1u << rslot;
                         }
                         load_stage<TM>(refill_dst, refill_A, refill_P, ld_stride10, ld_r0);
-                        cp_async_arrive(full_bar + rslot);
+                        ring_full_arrive(full_bar + rslot);
                     }
                     const int chunk = (s_lo + s) * (KS / KC) + ch;
                     if (kBanded && (chunk < c_lo || chunk >= c_hi)) continue;     // outside the window (CTA-uniform)
@@ -622,7 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                 // for stage s + 3) is going to wait for it, so every barrier phase has its waiters
                 if (s + 3 < nstages) {
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(empty_bar + slot);
+                    if (lane == 0) ring_empty_arrive(empty_bar + slot);
                 }
             }
             // The emission tile was copied with the step's first stage, whose full-barrier every thread
@@ -827,6 +824,7 @@ static cudaError_t launch_tiled_t(const ForwardArgs &a, cudaStream_t stream) {
     constexpr int TM = tile_rows(M);
     TiledParams p{};
     p.observation = a.observation;
+    p.obs_dtype = a.obs_dtype;
     p.transition = a.ws.transition_pad;
     p.initial = a.initial;
     p.frames = a.ws.frames;

@@ -30,7 +30,10 @@ constexpr int kWideThreads = 512;
 constexpr int kWideWarps = kWideThreads / kWarp;
 
 struct WideParams {
-    const float *observation;   // (B,T,S)
+    const float *observation;   // (B,T,S); 2-byte elements when obs_dtype != 0
+    int obs_dtype;              // 0 fp32, 1 fp16, 2 bf16
+    float *checkpoints;         // (B, ck_rows, S) or null: P_t for t = k * checkpoint_every
+    int64_t checkpoint_every, ck_rows;
     const float *transition;    // padded copy (SJ, LDP), -inf outside (S,S)
     const float *initial;       // (S,)
     const int32_t *frames;      // (B,)
@@ -122,10 +125,10 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
             for (int b = warp; b < nb; b += kWideWarps) {
                 const int item = slot_item[b];
                 float *dst0 = p.score0 + (int64_t)(first + b) * LDP;
-                const float *obs = p.observation + (int64_t)item * p.T * S;
+                const int64_t obs0 = (int64_t)item * p.T * S;
                 for (int c = j_begin + lane; c < c_end; c += kWarp) {
                     if (c < S) {
-                        dst0[c] = convert_observation<kFlags>(obs[c]) + p.initial[c];
+                        dst0[c] = convert_observation<kFlags>(load_observation(p.observation, obs0 + c, p.obs_dtype)) + p.initial[c];
                     } else {
                         dst0[c] = 0.f;                   // padding stays finite in both buffers
                         dst0[c + p.score_stride] = 0.f;
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
                 if (lane < nbw) {
                     const int item = slot_item[b0 + lane];
                     emit = t < slot_frames[b0 + lane]
-                        ? convert_observation<kFlags>(__ldg(p.observation + ((int64_t)item * p.T + t) * S + j))
+                        ? convert_observation<kFlags>(load_observation(p.observation, ((int64_t)item * p.T + t) * S + j, p.obs_dtype))
                         : __ldcg(P_cur + (int64_t)(b0 + lane) * LDP + j);
                 }
                 float best[BW];
@@ -225,8 +228,11 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
                         const int bb = b0 + b;
                         const bool live = t < slot_frames[bb];
                         P_new[(int64_t)bb * LDP + j] = live ? e + v : e;         // viterbi.cpp:102 / carried
-                        if (live)
+                        if (live) {
                             p.backptr[((int64_t)slot_item[bb] * p.T + t) * S + j] = (uint16_t)min(arg, S - 1);
+                            if (p.checkpoints && t % p.checkpoint_every == 0)
+                                p.checkpoints[((int64_t)slot_item[bb] * p.ck_rows + (t / p.checkpoint_every - 1)) * S + j] = e + v;
+                        }
                     }
                 }
             }
@@ -329,6 +335,10 @@ cudaError_t launch_forward_wide(const ForwardArgs &a, cudaStream_t stream) {
     const WideGeometry g = wide_geometry(a.B, a.S, a.sm_count);
     WideParams p{};
     p.observation = a.observation;
+    p.obs_dtype = a.obs_dtype;
+    p.checkpoints = a.checkpoints;
+    p.checkpoint_every = a.checkpoint_every > 0 ? a.checkpoint_every : 1;
+    p.ck_rows = a.checkpoints ? (a.T - 1) / a.checkpoint_every : 0;
     p.transition = a.ws.transition_pad;
     p.initial = a.initial;
     p.frames = a.ws.frames;

@@ -33,4 +33,25 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, unsigned parity) {
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// Ring synchronisation of the tiled / streamed-split kernels.  Shipped build: mbarriers -- every thread's
+// cp.async copies arrive on full[slot] when they land, every warp arrives on empty[slot] when it has read
+// the stage, so warps may drift apart by up to a stage.  -DTORBI_RING_SYNCTHREADS (debug build of
+// tools/sanitize.sh only) replaces all four by cp.async.wait_all + __syncthreads at the same program
+// points: the same copy / read schedule with synchronisation compute-sanitizer's racecheck can model
+// (it does not track non-bulk cp.async completion through mbarriers and reports those pairs as hazards).
+#ifdef TORBI_RING_SYNCTHREADS
+__device__ __forceinline__ void ring_full_arrive(u64 *) {}
+__device__ __forceinline__ void ring_full_wait(u64 *, unsigned) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+}
+__device__ __forceinline__ void ring_empty_arrive(u64 *) {}
+__device__ __forceinline__ void ring_empty_wait(u64 *, unsigned) { __syncthreads(); }
+#else
+__device__ __forceinline__ void ring_full_arrive(u64 *bar) { cp_async_arrive(bar); }
+__device__ __forceinline__ void ring_full_wait(u64 *bar, unsigned parity) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void ring_empty_arrive(u64 *bar) { mbar_arrive(bar); }
+__device__ __forceinline__ void ring_empty_wait(u64 *bar, unsigned parity) { mbar_wait(bar, parity); }
+#endif
+
 }  // namespace torbi_b200

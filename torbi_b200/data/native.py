@@ -31,11 +31,12 @@ def inspect(files: Sequence, threads: int = 0):
 
 
 def load_batch(files: Sequence, pin_memory: bool = False, threads: int = 0, out: torch.Tensor = None):
-    """Zero-padded fp32 (B, Tmax, S) batch of 2-D posteriorgram files plus their frame counts --
-    what Dataset + collate() produce (data/dataset.py:17-22, collate.py:19-33), assembled by
-    the native reader.  `out`: a flat (pinned) fp32 buffer to carve the batch from, if big enough.
-    Returns (observation, batch_frames) or None when the batch needs the generic path (files of
-    mixed dtype / width, or not 2-D)."""
+    """Zero-padded (B, Tmax, S) batch of 2-D posteriorgram files plus their frame counts -- what
+    Dataset + collate() produce (data/dataset.py:17-22, collate.py:19-33), assembled by the native
+    reader in the files' own dtype: fp32, or fp16 / bf16 (kept at 2 bytes per element all the way
+    to the kernel's observation load).  `out`: a flat (pinned) fp32 buffer to carve the batch
+    from, if big enough.  Returns (observation, batch_frames) or None when the batch needs the
+    generic path (files of mixed or other dtypes, mixed widths, or not 2-D)."""
     infos = inspect(files, threads)
     fallback = [i for i, info in enumerate(infos) if info.status != _ffi.PT_OK]
     loaded = {i: torch.load(files[i], map_location='cpu') for i in fallback}
@@ -47,22 +48,24 @@ def load_batch(files: Sequence, pin_memory: bool = False, threads: int = 0, out:
         else:
             shapes.append(tuple(info.shape[:info.ndim]))
             dtypes.add(DTYPES[info.dtype])
-    if dtypes != {torch.float32} or any(len(shape) != 2 for shape in shapes) or \
-            len({shape[1] for shape in shapes}) != 1:
+    if len(dtypes) != 1 or not dtypes <= {torch.float32, torch.float16, torch.bfloat16} or \
+            any(len(shape) != 2 for shape in shapes) or len({shape[1] for shape in shapes}) != 1:
         return None
+    dtype = next(iter(dtypes))
+    itemsize = 4 if dtype == torch.float32 else 2
     states = shapes[0][1]
     batch_frames = torch.tensor([shape[0] for shape in shapes])
     max_frames = int(batch_frames.max())
     numel = len(files) * max_frames * states
-    if out is not None and out.numel() >= numel:
-        observation = out[:numel].view(len(files), max_frames, states)
+    if out is not None and out.numel() * out.element_size() >= numel * itemsize:
+        observation = out.view(dtype)[:numel].view(len(files), max_frames, states)
     else:
-        observation = torch.empty((len(files), max_frames, states), dtype=torch.float32, pin_memory=pin_memory)
+        observation = torch.empty((len(files), max_frames, states), dtype=dtype, pin_memory=pin_memory)
     native = [i for i in range(len(files)) if i not in loaded]
     if native:
         array, _keep = _paths([files[i] for i in native])
         native_infos = (_ffi.PtInfo * len(native))(*[infos[i] for i in native])
-        row_bytes = max_frames * states * 4
+        row_bytes = max_frames * states * itemsize
         destinations = (ctypes.c_void_p * len(native))(*[observation.data_ptr() + i * row_bytes for i in native])
         capacities = (ctypes.c_int64 * len(native))(*([row_bytes] * len(native)))
         failed = _ffi.library().torbi_b200_pt_read(array, native_infos, len(native), destinations, capacities, threads)

@@ -26,11 +26,22 @@ def _check_inputs(observation, transition, initial):
         raise ValueError(f'transition must have shape ({states}, {states}), got {tuple(transition.shape)}')
     if tuple(initial.shape) != (states,):
         raise ValueError(f'initial must have shape ({states},), got {tuple(initial.shape)}')
-    for name, tensor in (('observation', observation), ('transition', transition), ('initial', initial)):
+    for name, tensor in (('transition', transition), ('initial', initial)):
         # the reference op raises on anything but fp32 (data_ptr<float>(), viterbi.cpp:46-50)
         if tensor.dtype != torch.float32:
             raise ValueError(f'{name} must be float32, got {tensor.dtype}')
+    # ... while the reference's from_probabilities casts the observation from any dtype (core.py:191):
+    # fp16 / bf16 observations are taken as they are and upcast inside the kernels
+    if observation.dtype not in _OBS_FLAGS:
+        raise ValueError(f'observation must be float32, float16 or bfloat16, got {observation.dtype}')
     return batch, frames, states
+
+
+_OBS_FLAGS = {torch.float32: 0, torch.float16: _ffi.OBS_F16, torch.bfloat16: _ffi.OBS_BF16}
+
+
+def _sm_count(device) -> int:
+    return torch.cuda.get_device_properties(device).multi_processor_count
 
 
 def decode(
@@ -42,12 +53,13 @@ def decode(
     *,
     flags: int = 0,
     return_posterior: bool = False,
+    checkpoint_every: Optional[int] = None,
 ) -> torch.Tensor:
     """Decode a time-varying categorical distribution
 
     Args:
-        observation: :math:`(N, T, S)` float32 CUDA tensor, log-probabilities
-            (or as described by `flags`)
+        observation: :math:`(N, T, S)` float32 (or float16 / bfloat16) CUDA tensor,
+            log-probabilities (or as described by `flags`)
         batch_frames :math:`(N)`
             Sequence length of each batch item
         transition :math:`(S, S)`
@@ -61,9 +73,14 @@ def decode(
             log-space conversion, kernel selection)
         return_posterior
             Also return the final forward scores :math:`(N, S)` float32
+        checkpoint_every
+            Also return the forward scores :math:`P_t` for t = k * checkpoint_every,
+            shape :math:`(N, (T - 1) // checkpoint_every, S)` float32 (rows at or past an
+            item's length are NaN) -- what lets a long decode be verified in segments
 
     Return:
         indices: :math:`(N, T)` int32 on the device of `observation`
+        (then the posterior and / or the checkpoints when requested)
     """
     del num_threads
     batch, frames, states = _check_inputs(observation, transition, initial)
@@ -79,23 +96,34 @@ def decode(
     transition = transition.contiguous()
     initial = initial.contiguous()
     host_frames = _host_frames(batch_frames, batch)
+    flags |= _OBS_FLAGS[observation.dtype]
     with torch.cuda.device(device):
         indices = torch.empty((batch, frames), dtype=torch.int32, device=device)
         posterior = torch.empty((batch, states), dtype=torch.float32, device=device) \
             if return_posterior else None
-        workspace_bytes = lib.torbi_b200_workspace_bytes(batch, frames, states, flags)
+        # sized for the kernel this call will use: uint16 backpointers for the wide / generic
+        # kernels (small batches, one long sequence), fp32 score history otherwise
+        workspace_bytes = lib.torbi_b200_workspace_bytes_planned(
+            host_frames.data_ptr(), batch, frames, states, flags, _sm_count(device))
         if workspace_bytes == 0:
             _ffi.check(_ffi.ERR_INVALID_ARGUMENT)
         workspace = torch.empty(workspace_bytes, dtype=torch.uint8, device=device)
         stream = torch.cuda.current_stream(device)
-        _ffi.check(lib.torbi_b200_decode(
-            observation.data_ptr(), host_frames.data_ptr(), transition.data_ptr(),
-            initial.data_ptr(), batch, frames, states, flags, indices.data_ptr(),
-            posterior.data_ptr() if return_posterior else None,
-            workspace.data_ptr(), workspace_bytes, stream.cuda_stream))
+        args = (observation.data_ptr(), host_frames.data_ptr(), transition.data_ptr(),
+                initial.data_ptr(), batch, frames, states, flags, indices.data_ptr(),
+                posterior.data_ptr() if return_posterior else None,
+                workspace.data_ptr(), workspace_bytes, stream.cuda_stream)
+        checkpoints = None
+        if checkpoint_every is None:
+            _ffi.check(lib.torbi_b200_decode(*args))
+        else:
+            checkpoints = torch.full((batch, max(0, (frames - 1) // max(1, checkpoint_every)), states),
+                                     float('nan'), dtype=torch.float32, device=device)
+            _ffi.check(lib.torbi_b200_decode_checkpointed(*args, checkpoints.data_ptr(), checkpoint_every))
         # the workspace goes back to torch's caching allocator here; it is only
         # handed out again in stream order, behind the kernels just enqueued
-    return (indices, posterior) if return_posterior else indices
+    out = (indices,) + ((posterior,) if return_posterior else ()) + ((checkpoints,) if checkpoints is not None else ())
+    return out if len(out) > 1 else indices
 
 
 def decode_host(
@@ -124,6 +152,7 @@ def decode_host(
     transition = transition.contiguous()
     initial = initial.contiguous()
     host_frames = _host_frames(batch_frames, batch)
+    flags |= _OBS_FLAGS[observation.dtype]
     if out is None:
         out = torch.empty((batch, frames), dtype=torch.int32)
     elif out.dtype != torch.int32 or tuple(out.shape) != (batch, frames) or not out.is_contiguous() \
