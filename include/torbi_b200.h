@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TORBI_B200_ABI_VERSION 2
+#define TORBI_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define TORBI_B200_API __attribute__((visibility("default")))
@@ -166,6 +166,41 @@ TORBI_B200_API int torbi_b200_decode_checkpointed(const void *observation, const
                       int64_t frames, int64_t states, uint32_t flags, int32_t *indices,
                       float *posterior, void *workspace, size_t workspace_bytes, void *stream,
                       float *checkpoints, int64_t checkpoint_every);
+
+/*
+ * The same decode on a PACKED (unpadded) batch -- the ragged layout of SURVEY 8b.  The reference pads
+ * every batch to its longest item (data/collate.py:26-31) and allocates a (batch, frames, states)
+ * trellis (viterbi.cpp:201-203); here item b occupies rows [item_row[b], item_row[b] + batch_frames[b])
+ * of one (rows, states) observation buffer, its decoded states land in the same rows of the (rows,)
+ * `indices`, and the score history / backpointers take rows * states entries instead of
+ * batch * max_frames * states.  Items may be any non-overlapping row ranges in any order (gaps are
+ * allowed: rows no item covers are neither read nor written), so the pieces of a chunked sequence
+ * (chunk.py:12-49) or the files of a batch are decoded where they lie, without a padded copy.
+ *
+ *   observation   device (rows, states) fp32 (fp16 / bf16 with TORBI_B200_OBS_F16 / _BF16)
+ *   item_row      HOST   (batch,) int64 first row of every item
+ *   batch_frames  HOST   (batch,) int32 rows of every item, each >= 1
+ *   indices       device (rows,) int32: indices[item_row[b] + t] = state of item b at frame t
+ *   workspace     device, >= torbi_b200_workspace_bytes_packed(...) for the same arguments
+ * Everything else as torbi_b200_decode.  Each item decodes exactly as it would alone.
+ */
+TORBI_B200_API int torbi_b200_decode_packed(const void *observation, const int64_t *item_row,
+                      const int32_t *batch_frames, const float *transition, const float *initial,
+                      int64_t batch, int64_t rows, int64_t states, uint32_t flags, int32_t *indices,
+                      float *posterior, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Workspace for torbi_b200_decode_packed (host logic only; 0 on invalid arguments, see
+ * torbi_b200_last_error). */
+TORBI_B200_API size_t torbi_b200_workspace_bytes_packed(const int64_t *item_row, const int32_t *batch_frames,
+                                                        int64_t batch, int64_t rows, int64_t states,
+                                                        uint32_t flags, int sm_count);
+
+/* torbi_b200_decode_packed for HOST buffers on one device (copies, decode and the copy back of the
+ * (rows,) indices inside the call; rows no item covers keep the caller's values). */
+TORBI_B200_API int torbi_b200_decode_host_packed(const void *observation, const int64_t *item_row,
+                      const int32_t *batch_frames, const float *transition, const float *initial,
+                      int64_t batch, int64_t rows, int64_t states, uint32_t flags, int32_t *indices,
+                      float *posterior, int device);
 
 /*
  * Decode a batch resident in HOST memory on one device: host->device copies,

@@ -344,3 +344,83 @@ def ring_stress_problem(oracle):
     frames[5] = 5999
     want_idx, want_post = oracle.c_decode(obs, frames, A, init, exact_scan=False, want_posterior=True)
     return obs, frames, A, init, want_idx, want_post
+
+
+# ---------------------------------------------------------------------------
+# packed (unpadded) layout
+# ---------------------------------------------------------------------------
+
+def _packed_problem(seed, lengths, S, gap_rows=(0, 3, 0, 1), transition='dense', quant=2):
+    """Items of the given lengths laid out in one (rows, S) buffer in a shuffled order with gaps."""
+    B, T = len(lengths), int(max(lengths))
+    obs, frames, A, init = random_problem(seed, B, T, S, quant=quant, transition=transition)
+    frames = np.asarray(lengths, np.int32)
+    rng = np.random.default_rng(seed)
+    placement = rng.permutation(B)
+    item_row = np.zeros(B, np.int64)
+    row = 0
+    for k, b in enumerate(placement):
+        row += gap_rows[k % len(gap_rows)]
+        item_row[b] = row
+        row += int(frames[b])
+    rows = row + 2
+    packed = np.full((rows, S), np.nan, np.float32)              # gaps hold NaN: they must never be read
+    for b in range(B):
+        packed[item_row[b]:item_row[b] + frames[b]] = obs[b, :frames[b]]
+    return obs, frames, A, init, packed, item_row, rows
+
+
+@pytest.mark.parametrize('kernel,flags', [
+    ('auto', 0), ('generic', _ffi.FORCE_GENERIC), ('wide', _ffi.FORCE_WIDE), ('tiled64', _ffi.TILE_ROWS_64),
+    ('tiled16bp', _ffi.TILE_ROWS_16 | _ffi.BACKPOINTERS), ('banded', _ffi.BANDED | _ffi.TILE_ROWS_32),
+    ('split', _ffi.FORCE_SPLIT), ('split_streamed', _ffi.FORCE_SPLIT | _ffi.SPLIT_STREAMED), ('cluster', _ffi.FORCE_CLUSTER)])
+@pytest.mark.parametrize('states', [1440, 333])
+def test_packed_layout_matches_oracle(states, kernel, flags, oracle):
+    """torbi_b200_decode_packed: ragged items anywhere in one (rows, S) buffer, every kernel; the
+    states of item b come back in its own rows, rows between items are left alone."""
+    rng = np.random.default_rng(states)
+    lengths = rng.integers(1, 40, size=70)
+    lengths[3], lengths[11] = 1, 39
+    obs, frames, A, init, packed, item_row, rows = _packed_problem(states + 1, lengths, states)
+    want, want_post = oracle.c_decode(obs, frames, A, init, exact_scan=False, want_posterior=True)
+    out = torch.full((rows,), -7, dtype=torch.int32, device='cuda:0')
+    got, post = torbi_b200.decode_packed(cuda(packed), torch.from_numpy(item_row), torch.from_numpy(frames), cuda(A), cuda(init),
+                                         flags=flags, return_posterior=True, out=out)
+    got = got.cpu().numpy()
+    covered = np.zeros(rows, bool)
+    for b in range(len(lengths)):
+        lo, hi = item_row[b], item_row[b] + frames[b]
+        assert np.array_equal(got[lo:hi], want[b, :frames[b]]), (kernel, b)
+        covered[lo:hi] = True
+    assert (got[~covered] == -7).all()
+    assert np.array_equal(bits(post.cpu().numpy()), bits(want_post))
+
+
+def test_packed_layout_long_item_uses_the_blocked_backtrace(oracle):
+    lengths = [17000, 300, 5]
+    obs, frames, A, init, packed, item_row, rows = _packed_problem(8, lengths, 256, transition='dense')
+    want = oracle.c_decode(obs, frames, A, init, exact_scan=False)
+    got = torbi_b200.decode_packed(cuda(packed), torch.from_numpy(item_row), torch.from_numpy(frames), cuda(A), cuda(init),
+                                   flags=_ffi.FORCE_WIDE).cpu().numpy()
+    assert _ffi.library().torbi_b200_last_backtrace().decode() == 'backtrace_blocked'
+    for b in range(3):
+        assert np.array_equal(got[item_row[b]:item_row[b] + frames[b]], want[b, :frames[b]])
+
+
+def test_packed_host_entry_and_validation(oracle):
+    lengths = [30, 12, 1, 25, 30, 7]
+    obs, frames, A, init, packed, item_row, rows = _packed_problem(21, lengths, 97, quant=None)
+    want = oracle.c_decode(obs, frames, A, init, exact_scan=False)
+    t = lambda x: torch.from_numpy(x)
+    out = torch.full((rows,), -3, dtype=torch.int32)
+    got = torbi_b200.decode_host_packed(t(np.nan_to_num(packed)), t(item_row), t(frames), t(A), t(init), gpu=0, out=out).numpy()
+    for b in range(len(lengths)):
+        assert np.array_equal(got[item_row[b]:item_row[b] + frames[b]], want[b, :frames[b]])
+    bad = item_row.copy()
+    bad[0] = bad[1]                                              # two items on the same rows
+    with pytest.raises(ValueError, match='overlap'):
+        torbi_b200.decode_packed(cuda(packed), t(bad), t(frames), cuda(A), cuda(init))
+    bad = item_row.copy()
+    bad[int(np.argmax(item_row))] = rows - 1                     # runs off the end
+    with pytest.raises(ValueError, match='leave the buffer'):
+        torbi_b200.decode_packed(cuda(packed), t(bad), t(frames), cuda(A), cuda(init))

@@ -16,5 +16,5 @@ fi
 for mode in ${MODES:-"" "--backpointers"} ${EXTRA_MODES}; do
   echo "== mode: ${mode:-score history}"
   TORBI_B200_LIBRARY="$PWD/$lib" python bench.py --steps 1 --warmup 1 --no-e2e \
-      --no-cpu-baseline $mode --batch ${BATCH:-512} --frames ${FRAMES:-500} | grep "^cta" | sort | uniq | head -8
+      --no-cpu-baseline --no-configs --no-strong $mode --batch ${BATCH:-512} --frames ${FRAMES:-500} | grep "^cta" | sort | uniq | head -8
 done

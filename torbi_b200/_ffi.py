@@ -36,7 +36,7 @@ FORCE_SPLIT = 1 << 17
 SPLIT_STREAMED = 1 << 18
 FORCE_CLUSTER = 1 << 19
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _p = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -51,6 +51,11 @@ SIGNATURES = {
     'torbi_b200_workspace_bytes_planned': (ctypes.c_size_t, [_p, _i64, _i64, _i64, ctypes.c_uint32, ctypes.c_int]),
     'torbi_b200_decode_checkpointed': (ctypes.c_int, [
         _p, _p, _p, _p, _i64, _i64, _i64, ctypes.c_uint32, _p, _p, _p, ctypes.c_size_t, _p, _p, _i64]),
+    'torbi_b200_decode_packed': (ctypes.c_int, [
+        _p, _p, _p, _p, _p, _i64, _i64, _i64, ctypes.c_uint32, _p, _p, _p, ctypes.c_size_t, _p]),
+    'torbi_b200_workspace_bytes_packed': (ctypes.c_size_t, [_p, _p, _i64, _i64, _i64, ctypes.c_uint32, ctypes.c_int]),
+    'torbi_b200_decode_host_packed': (ctypes.c_int, [
+        _p, _p, _p, _p, _p, _i64, _i64, _i64, ctypes.c_uint32, _p, _p, ctypes.c_int]),
     'torbi_b200_decode_host': (ctypes.c_int, [
         _p, _p, _p, _p, _i64, _i64, _i64, ctypes.c_uint32, _p, _p, ctypes.c_int]),
     'torbi_b200_decode_host_multi': (ctypes.c_int, [

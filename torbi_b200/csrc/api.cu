@@ -149,7 +149,7 @@ int torbi_b200_device_count(void) {
 
 size_t torbi_b200_workspace_bytes(int64_t B, int64_t T, int64_t S, uint32_t flags) {
     if (validate_shape(B, T, S) != TORBI_B200_OK) return 0;
-    return carve_workspace(nullptr, B, T, S, workspace_has_history(flags)).bytes;
+    return carve_workspace(nullptr, B, B * T, S, workspace_has_history(flags)).bytes;
 }
 
 }  // extern "C"
@@ -237,14 +237,28 @@ struct Plan {
     bool history = false;
     int64_t max_frames = 0;
     std::vector<int32_t> order;  // (pad_batch,) items longest first, -1 = empty slot
+    // first row of every item in observation / history / backpointers / indices: b * T in the padded
+    // (B,T,S) layout, the caller's offsets in the packed (rows,S) one
+    std::vector<int64_t> item_row;
+    int64_t rows = 0;            // rows of the observation buffer (B * T when padded)
+    bool packed = false;
     size_t workspace_bytes = 0;
 };
 
+// `item_row` == nullptr: padded layout, `T` frames per item.  Otherwise the packed layout: `rows` rows in
+// all, item b occupies rows [item_row[b], item_row[b] + batch_frames[b]); T is ignored.
 int make_plan(const int32_t *batch_frames, int64_t B, int64_t T, int64_t S, uint32_t flags, int sm_count,
-              Plan *plan) {
+              Plan *plan, const int64_t *item_row = nullptr, int64_t rows = 0) {
+    if (!batch_frames) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+    plan->packed = item_row != nullptr;
+    if (plan->packed) {
+        if (B < 1 || rows < 1)
+            return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "batch and rows must be >= 1 (got %lld, %lld)", (long long)B, (long long)rows);
+        T = 1;
+        for (int64_t b = 0; b < B; ++b) T = std::max<int64_t>(T, batch_frames[b]);
+    }
     int rc = validate_shape(B, T, S);
     if (rc) return rc;
-    if (!batch_frames) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "NULL pointer argument");
     if ((flags & TORBI_B200_OBS_F16) && (flags & TORBI_B200_OBS_BF16))
         return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "TORBI_B200_OBS_F16 and TORBI_B200_OBS_BF16 are exclusive");
     plan->max_frames = 0;
@@ -254,6 +268,28 @@ int make_plan(const int32_t *batch_frames, int64_t B, int64_t T, int64_t S, uint
             return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "batch_frames[%lld] = %d outside [1, %lld]",
                         (long long)b, batch_frames[b], (long long)T);
         plan->max_frames = std::max<int64_t>(plan->max_frames, batch_frames[b]);
+    }
+    plan->item_row.resize(B);
+    if (plan->packed) {
+        // every item inside the buffer, no two items sharing a row (the score history / backpointers
+        // and the output use the same row numbering)
+        std::vector<int64_t> by_row(B);
+        std::iota(by_row.begin(), by_row.end(), 0);
+        std::sort(by_row.begin(), by_row.end(), [&](int64_t x, int64_t y) { return item_row[x] < item_row[y]; });
+        int64_t end = 0;
+        for (int64_t k = 0; k < B; ++k) {
+            const int64_t b = by_row[k];
+            if (item_row[b] < end || item_row[b] + batch_frames[b] > rows)
+                return fail(TORBI_B200_ERR_INVALID_ARGUMENT,
+                            "item %lld: rows [%lld, %lld) overlap another item or leave the buffer of %lld rows",
+                            (long long)b, (long long)item_row[b], (long long)(item_row[b] + batch_frames[b]), (long long)rows);
+            end = item_row[b] + batch_frames[b];
+            plan->item_row[b] = item_row[b];
+        }
+        plan->rows = rows;
+    } else {
+        for (int64_t b = 0; b < B; ++b) plan->item_row[b] = b * T;
+        plan->rows = B * T;
     }
     plan->order.assign(pad_batch(B), -1);
     std::iota(plan->order.begin(), plan->order.begin() + B, 0);
@@ -266,7 +302,7 @@ int make_plan(const int32_t *batch_frames, int64_t B, int64_t T, int64_t S, uint
     a.flags = flags;
     a.sm_count = sm_count;
     // layout only, never dereferenced: the `supported` predicates only look at shapes
-    a.ws = carve_workspace(reinterpret_cast<void *>(uintptr_t(256)), B, T, S, workspace_has_history(flags));
+    a.ws = carve_workspace(reinterpret_cast<void *>(uintptr_t(256)), B, plan->rows, S, workspace_has_history(flags));
     a.observation = reinterpret_cast<const float *>(uintptr_t(256));
     rc = choose_kernel(a, sorted, flags, &plan->choice);
     if (rc) return rc;
@@ -274,7 +310,7 @@ int make_plan(const int32_t *batch_frames, int64_t B, int64_t T, int64_t S, uint
     plan->tile_rows = a.tile_rows;
     plan->history = plan->choice == kSplit || plan->choice == kCluster ||
                     (plan->choice == kTiled && workspace_has_history(flags));
-    plan->workspace_bytes = carve_workspace(nullptr, B, T, S, plan->history).bytes;
+    plan->workspace_bytes = carve_workspace(nullptr, B, plan->rows, S, plan->history).bytes;
     return TORBI_B200_OK;
 }
 
@@ -287,6 +323,9 @@ struct DecodeOptions {
     float *checkpoints = nullptr;
     int64_t checkpoint_every = 0;
     const Plan *plan = nullptr;  // made by the caller already (host entry)
+    // packed layout (torbi_b200_decode_packed): host (B,) first rows and the row count; T is ignored
+    const int64_t *item_row = nullptr;
+    int64_t rows = 0;
 };
 
 int decode_device(const void *observation, const int32_t *batch_frames,
@@ -304,18 +343,23 @@ int decode_device(const void *observation, const int32_t *batch_frames,
     if (rc) return rc;
     Plan own_plan;
     if (!opt.plan) {
-        rc = make_plan(batch_frames, B, T, S, flags, info.sm_count, &own_plan);
+        rc = make_plan(batch_frames, B, T, S, flags, info.sm_count, &own_plan, opt.item_row, opt.rows);
         if (rc) return rc;
     }
     const Plan &plan = opt.plan ? *opt.plan : own_plan;
     flags = plan.flags;
+    if (plan.packed) {
+        T = plan.max_frames;
+        if (opt.checkpoints)
+            return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "checkpoints are not available in the packed layout");
+    }
     if (opt.checkpoints && opt.checkpoint_every < 1)
         return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "checkpoint_every must be >= 1");
     if (reinterpret_cast<uintptr_t>(workspace) % 256)
         return fail(TORBI_B200_ERR_WORKSPACE, "workspace must be 256-byte aligned");
     // the kernel is chosen first, so a call that ends up on the wide / generic kernel (uint16
     // backpointers) only needs half the trailing region of a score-history call
-    Workspace ws = carve_workspace(workspace, B, T, S, plan.history);
+    Workspace ws = carve_workspace(workspace, B, plan.rows, S, plan.history);
     if (workspace_bytes < ws.bytes)
         return fail(TORBI_B200_ERR_WORKSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, ws.bytes);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -325,6 +369,8 @@ int decode_device(const void *observation, const int32_t *batch_frames,
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(ws.order, plan.order.data(), sizeof(int32_t) * plan.order.size(),
                             cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(ws.item_row, plan.item_row.data(), sizeof(int64_t) * B, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(ws.sync, 0, sizeof(uint32_t) * kSyncWords, stream);
     if (e != cudaSuccess) return fail_cuda(e, "stage batch_frames");
     // (pageable host memory: the async copies have been staged by the time cudaMemcpyAsync returns)
@@ -385,15 +431,16 @@ int decode_device(const void *observation, const int32_t *batch_frames,
     }
     if (timed) cudaEventRecord(g_timing.ev[1], stream);
     const bool history = plan.history;
+    const int64_t T_out = plan.packed ? 0 : T;           // 0: indices are packed like the observations
     int backtrace_launches = 1;
     g_last_backtrace = history ? "backtrace_recompute" : "backtrace";
     if (history) {
-        e = launch_backtrace_recompute(ws, indices, B, T, S, stream);
+        e = launch_backtrace_recompute(ws, indices, B, T_out, S, stream);
     } else if (plan.max_frames >= kWindowedBacktraceMinFrames) {
         g_last_backtrace = "backtrace_blocked";
-        e = launch_backtrace_blocked(ws, indices, B, T, S, plan.max_frames, &backtrace_launches, stream);
+        e = launch_backtrace_blocked(ws, indices, B, T_out, S, plan.max_frames, &backtrace_launches, stream);
     } else {
-        e = launch_backtrace(ws, indices, B, T, S, stream);
+        e = launch_backtrace(ws, indices, B, T_out, S, stream);
     }
     if (e != cudaSuccess) return fail_cuda(e, g_last_backtrace);
     if (timed) {
@@ -431,6 +478,34 @@ int torbi_b200_decode_checkpointed(const void *observation, const int32_t *batch
         return decode_device(observation, batch_frames, transition, initial, B, T, S, flags, indices,
                              posterior, workspace, workspace_bytes, stream, opt);
     });
+}
+
+int torbi_b200_decode_packed(const void *observation, const int64_t *item_row, const int32_t *batch_frames,
+                             const float *transition, const float *initial, int64_t B, int64_t rows,
+                             int64_t S, uint32_t flags, int32_t *indices, float *posterior,
+                             void *workspace, size_t workspace_bytes, void *stream) {
+    return guarded([&] {
+        if (!item_row) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+        DecodeOptions opt;
+        opt.item_row = item_row;
+        opt.rows = rows;
+        return decode_device(observation, batch_frames, transition, initial, B, /*T=*/1, S, flags, indices,
+                             posterior, workspace, workspace_bytes, stream, opt);
+    });
+}
+
+size_t torbi_b200_workspace_bytes_packed(const int64_t *item_row, const int32_t *batch_frames, int64_t B,
+                                         int64_t rows, int64_t S, uint32_t flags, int sm_count) {
+    g_error[0] = 0;
+    if (sm_count < 1 || !item_row) return 0;
+    try {
+        Plan plan;
+        if (make_plan(batch_frames, B, 1, S, flags, sm_count, &plan, item_row, rows) != TORBI_B200_OK) return 0;
+        return plan.workspace_bytes;
+    } catch (...) {
+        fail(TORBI_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
+        return 0;
+    }
 }
 
 size_t torbi_b200_workspace_bytes_planned(const int32_t *batch_frames, int64_t B, int64_t T, int64_t S,
@@ -515,6 +590,8 @@ struct DeviceGuard {
     }
 };
 
+int arena_reserve(Arena *arena, int device, size_t total);
+
 // Decode `count` items (given by index into the caller's batch) on one device.
 int decode_items_on_device(const void *observation_, const int32_t *batch_frames,
                            const float *transition, const float *initial,
@@ -548,27 +625,8 @@ int decode_items_on_device(const void *observation_, const int32_t *batch_frames
     const size_t total = obs_bytes + tr_bytes + init_bytes + idx_bytes + post_bytes + ws_bytes + 256;
 
     cudaError_t e;
-    if (!arena->stream) {
-        e = cudaStreamCreateWithFlags(&arena->stream, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&arena->copy_stream, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&arena->reset_event, cudaEventDisableTiming);
-        if (e == cudaSuccess)
-            e = cudaHostAlloc(reinterpret_cast<void **>(&arena->ready_host),
-                              sizeof(int32_t) * kMaxChunks, cudaHostAllocDefault);
-        if (e != cudaSuccess) return fail_cuda(e, "create streams");
-    }
-    if (arena->bytes < total) {
-        if (arena->base) cudaFree(arena->base);
-        arena->base = nullptr;
-        arena->bytes = 0;
-        e = cudaMalloc(&arena->base, total);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            return fail(TORBI_B200_ERR_OUT_OF_MEMORY, "device %d: cannot allocate %zu bytes: %s",
-                        device, total, cudaGetErrorString(e));
-        }
-        arena->bytes = total;
-    }
+    rc = arena_reserve(arena, device, total);
+    if (rc) return rc;
     char *p = static_cast<char *>(arena->base);
     char *d_obs = p; p += obs_bytes;
     float *d_tr = reinterpret_cast<float *>(p); p += tr_bytes;
@@ -674,6 +732,92 @@ int decode_items_on_device(const void *observation_, const int32_t *batch_frames
     return TORBI_B200_OK;
 }
 
+// Streams, the pinned ready words and at least `total` bytes of device memory for this device's arena.
+int arena_reserve(Arena *arena, int device, size_t total) {
+    cudaError_t e;
+    if (!arena->stream) {
+        e = cudaStreamCreateWithFlags(&arena->stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&arena->copy_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&arena->reset_event, cudaEventDisableTiming);
+        if (e == cudaSuccess)
+            e = cudaHostAlloc(reinterpret_cast<void **>(&arena->ready_host),
+                              sizeof(int32_t) * kMaxChunks, cudaHostAllocDefault);
+        if (e != cudaSuccess) return fail_cuda(e, "create streams");
+    }
+    if (arena->bytes < total) {
+        if (arena->base) cudaFree(arena->base);
+        arena->base = nullptr;
+        arena->bytes = 0;
+        e = cudaMalloc(&arena->base, total);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(TORBI_B200_ERR_OUT_OF_MEMORY, "device %d: cannot allocate %zu bytes: %s",
+                        device, total, cudaGetErrorString(e));
+        }
+        arena->bytes = total;
+    }
+    return TORBI_B200_OK;
+}
+
+// Packed layout from host memory: one copy in of the (rows, S) observations (no padding crosses the
+// bus), decode, one copy out of the (rows,) indices.
+int decode_packed_on_device(const void *observation, const int64_t *item_row, const int32_t *batch_frames,
+                            const float *transition, const float *initial, int64_t B, int64_t rows, int64_t S,
+                            uint32_t flags, int32_t *indices, float *posterior, int device) {
+    DeviceGuard guard(device);
+    DeviceInfo info;
+    int rc = device_info(device, &info);
+    if (rc) return rc;
+    Arena *arena = arena_for(device);
+    std::lock_guard<std::mutex> lock(arena->busy);
+    Plan plan;
+    rc = make_plan(batch_frames, B, 1, S, flags, info.sm_count, &plan, item_row, rows);
+    if (rc) return rc;
+    const size_t elem = (flags & (TORBI_B200_OBS_F16 | TORBI_B200_OBS_BF16)) ? 2 : 4;
+    const size_t obs_bytes = align_up(elem * rows * S, 256);
+    const size_t tr_bytes = align_up(sizeof(float) * S * S, 256);
+    const size_t init_bytes = align_up(sizeof(float) * S, 256);
+    const size_t idx_bytes = align_up(sizeof(int32_t) * rows, 256);
+    const size_t post_bytes = posterior ? align_up(sizeof(float) * B * S, 256) : 0;
+    const size_t ws_bytes = plan.workspace_bytes;
+    rc = arena_reserve(arena, device, obs_bytes + tr_bytes + init_bytes + idx_bytes + post_bytes + ws_bytes + 256);
+    if (rc) return rc;
+    char *p = static_cast<char *>(arena->base);
+    char *d_obs = p; p += obs_bytes;
+    float *d_tr = reinterpret_cast<float *>(p); p += tr_bytes;
+    float *d_init = reinterpret_cast<float *>(p); p += init_bytes;
+    int32_t *d_idx = reinterpret_cast<int32_t *>(p); p += idx_bytes;
+    float *d_post = posterior ? reinterpret_cast<float *>(p) : nullptr; p += post_bytes;
+    void *d_ws = p;
+    cudaStream_t stream = arena->stream;
+    struct Drain {
+        cudaStream_t stream;
+        bool armed = true;
+        ~Drain() {
+            if (!armed) return;
+            cudaStreamSynchronize(stream);
+            cudaGetLastError();
+        }
+    } drain{stream};
+    cudaError_t e = cudaMemcpyAsync(d_tr, transition, sizeof(float) * S * S, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_init, initial, sizeof(float) * S, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_obs, observation, elem * rows * S, cudaMemcpyHostToDevice, stream);
+    // rows no item covers keep whatever the caller's buffer holds: bring it along
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, indices, sizeof(int32_t) * rows, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return fail_cuda(e, "host->device copy");
+    DecodeOptions opt;
+    opt.plan = &plan;
+    rc = decode_device(d_obs, batch_frames, d_tr, d_init, B, 1, S, flags, d_idx, d_post, d_ws, ws_bytes, stream, opt);
+    if (rc) return rc;
+    e = cudaMemcpyAsync(indices, d_idx, sizeof(int32_t) * rows, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && posterior)
+        e = cudaMemcpyAsync(posterior, d_post, sizeof(float) * B * S, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return fail_cuda(e, "device->host copy / synchronize");
+    drain.armed = false;
+    return TORBI_B200_OK;
+}
+
 int validate_host_args(const void *observation, const int32_t *batch_frames,
                        const float *transition, const float *initial, int64_t B, int64_t T,
                        int64_t S, const int32_t *indices) {
@@ -751,6 +895,18 @@ int torbi_b200_decode_host_multi(const void *observation, const int32_t *batch_f
     for (int k = 0; k < n; ++k)
         if (status[k]) return fail(status[k], "device %d: %s", devices[k], message[k].c_str());
     return TORBI_B200_OK;
+    });
+}
+
+int torbi_b200_decode_host_packed(const void *observation, const int64_t *item_row, const int32_t *batch_frames,
+                                  const float *transition, const float *initial, int64_t B, int64_t rows,
+                                  int64_t S, uint32_t flags, int32_t *indices, float *posterior, int device) {
+    g_error[0] = 0;
+    if (!observation || !item_row || !batch_frames || !transition || !initial || !indices)
+        return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+    return guarded([&] {
+        return decode_packed_on_device(observation, item_row, batch_frames, transition, initial, B, rows, S, flags,
+                                       indices, posterior, device);
     });
 }
 

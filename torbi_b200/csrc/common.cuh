@@ -71,7 +71,7 @@ __device__ __forceinline__ float load_observation(const void *base, int64_t inde
 template <int TM, int TN, int kThreads>
 __device__ __forceinline__ void load_emission_tile_plain(float *tile, const void *observation, int dtype,
                                                          const int *slot_item, const int *slot_frames,
-                                                         int64_t T, int S, int t, int j0) {
+                                                         const int64_t *slot_row, int S, int t, int j0) {
     const bool half4 = dtype != 0 && (S % 4) == 0 && (reinterpret_cast<uintptr_t>(observation) & 7) == 0;
     if (half4) {
         // four 2-byte elements per 8-byte load
@@ -80,7 +80,7 @@ __device__ __forceinline__ void load_emission_tile_plain(float *tile, const void
             const int item = slot_item[r];
             if (item >= 0 && t < slot_frames[r] && j0 + c4 * 4 < S) {
                 const uint2 raw = __ldcg(reinterpret_cast<const uint2 *>(
-                    static_cast<const unsigned short *>(observation) + ((int64_t)item * T + t) * S + j0 + c4 * 4));
+                    static_cast<const unsigned short *>(observation) + (slot_row[r] + t) * S + j0 + c4 * 4));
                 float4 v;
                 v.x = half_bits_to_float((unsigned short)(raw.x & 0xffffu), dtype);
                 v.y = half_bits_to_float((unsigned short)(raw.x >> 16), dtype);
@@ -94,7 +94,7 @@ __device__ __forceinline__ void load_emission_tile_plain(float *tile, const void
             const int r = idx / TN, c = idx % TN;
             const int item = slot_item[r];
             if (item >= 0 && t < slot_frames[r] && j0 + c < S)
-                tile[idx] = load_observation(observation, ((int64_t)item * T + t) * S + j0 + c, dtype);
+                tile[idx] = load_observation(observation, (slot_row[r] + t) * S + j0 + c, dtype);
         }
     }
 }
@@ -111,6 +111,8 @@ struct Workspace {
     int32_t *frames;        // (B,)  device copy of batch_frames
     int32_t *order;         // (B,)  items sorted by length, longest first
     int32_t *final_state;   // (B,)  argmax of the final forward scores
+    int64_t *item_row;      // (B,)  first row of each item in `observation` / history / backpointers / `indices`:
+                            //       b * T in the padded (B,T,S) layout, the caller's offsets in the packed one
     uint32_t *sync;         // scheduling / barrier words (zeroed per call)
     float *score[4];        // rotating forward-score buffers, (pad_batch, padded_sources) each
     float *block_max;       // 3 x (pad_batch, padded_sources / 16): max of each 16-state block of the rotating
@@ -144,8 +146,9 @@ inline bool workspace_has_history(uint32_t flags) { return !(flags & TORBI_B200_
 // `history` = the trailing region holds fp32 forward scores (4 bytes per (b,t,s): tiled kernel in
 // score-history mode, split / cluster kernels) rather than uint16 backpointers (2 bytes: wide and generic
 // kernels, tiled kernel in backpointer mode).  Everything before that region has the same layout
-// either way, so the region can be sized after the kernel has been chosen.
-inline Workspace carve_workspace(void *base, int64_t B, int64_t T, int64_t S, bool history) {
+// either way, so the region can be sized after the kernel has been chosen.  `rows` = rows of the
+// observation buffer: B * T in the padded layout, the packed total otherwise.
+inline Workspace carve_workspace(void *base, int64_t B, int64_t rows, int64_t S, bool history) {
     Workspace w{};
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -157,6 +160,7 @@ inline Workspace carve_workspace(void *base, int64_t B, int64_t T, int64_t S, bo
     w.frames = static_cast<int32_t *>(take(sizeof(int32_t) * B));
     w.order = static_cast<int32_t *>(take(sizeof(int32_t) * Bp));
     w.final_state = static_cast<int32_t *>(take(sizeof(int32_t) * B));
+    w.item_row = static_cast<int64_t *>(take(sizeof(int64_t) * B));
     w.sync = static_cast<uint32_t *>(take(sizeof(uint32_t) * kSyncWords));
     w.score[0] = static_cast<float *>(take(sizeof(float) * Bp * Sp));
     w.score[1] = static_cast<float *>(take(sizeof(float) * Bp * Sp));
@@ -165,7 +169,7 @@ inline Workspace carve_workspace(void *base, int64_t B, int64_t T, int64_t S, bo
     w.block_max = static_cast<float *>(take(sizeof(float) * 3 * Bp * (Sp / 16)));
     w.transition_pad = static_cast<float *>(take(sizeof(float) * padded_dests(S) * Sp));
     w.backptr = static_cast<uint16_t *>(
-        take((history ? sizeof(float) : sizeof(uint16_t)) * B * T * S));
+        take((history ? sizeof(float) : sizeof(uint16_t)) * rows * S));
     w.bytes = off;
     return w;
 }

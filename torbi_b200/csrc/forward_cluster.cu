@@ -51,20 +51,20 @@ constexpr int kMaxBatches = 24;                   // batches a group interleaves
 constexpr int kSyncStride = 8;                    // words between counters: one 32-byte sector each
 
 struct ClusterParams {
-    const float *observation;   // (B,T,S); 2-byte elements when obs_dtype != 0
+    const float *observation;   // (rows,S), item b at rows item_row[b] ..; 2-byte elements when obs_dtype != 0
     int obs_dtype;
     const float *transition;    // padded copy (SJ, LDP), -inf outside (S,S)
     const float *initial;       // (S,)
     const int32_t *frames;      // (B,)
+    const int64_t *item_row;    // (B,) first row of each item in observation / history
     const int32_t *order;       // (Bpad,) items longest first, -1 = empty slot
     float *score0;              // 2 alternating buffers (Bpad, LDP), `score_stride` floats apart
     int64_t score_stride;
-    float *history;             // (B,T,S) fp32: every P_t
+    float *history;             // (rows,S) fp32: every P_t
     float *posterior;           // (B,S) or null
     int32_t *final_state;       // (B,)
     unsigned *sync;             // counters, kSyncStride words apart: [1 + batch] publish counts, then one per group
     const int32_t *frames_ready;
-    int64_t T;
     int S, LDP, NJT, NG, num_batches;
     int nk[kWarps];             // k-steps of each warp within its CTA's half of the sources
 };
@@ -72,7 +72,7 @@ struct ClusterParams {
 size_t cluster_smem_bytes(int ldp) {
     return sizeof(float) * (kWarps * kSlots * kSlotFloats + TN * (ldp / 2 + 4)) +
            sizeof(float4) * (2 * kWarps * kReduceThreads + 2 * kReduceThreads) +
-           sizeof(int) * (2 * kMaxBatches * TM + kMaxBatches) + sizeof(u64) * 2 + 16;
+           sizeof(int) * (4 * kMaxBatches * TM + kMaxBatches) + sizeof(u64) * 2 + 16;
 }
 
 __device__ __forceinline__ u64 add2(u64 a, u64 b) {     // two fp32 adds (FADD2), IEEE rn
@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
     float *A_res = ring + kWarps * kSlots * kSlotFloats;        // [TN][LDA]
     float4 *partial = reinterpret_cast<float4 *>(A_res + TN * LDA);   // [2][warp][160] per-warp maxima
     float4 *inbox = partial + 2 * kWarps * kReduceThreads;      // [2][160] the peer's reduced half
-    int *s_item = reinterpret_cast<int *>(inbox + 2 * kReduceThreads);   // [kMaxBatches][TM]
+    int64_t *s_row = reinterpret_cast<int64_t *>(inbox + 2 * kReduceThreads);   // [kMaxBatches][TM] first row of the item
+    int *s_item = reinterpret_cast<int *>(s_row + kMaxBatches * TM);     // [kMaxBatches][TM]
     int *s_frames = s_item + kMaxBatches * TM;                  // [kMaxBatches][TM]
     int *s_len = s_frames + kMaxBatches * TM;                   // [kMaxBatches] frames of the batch's longest item
     u64 *inbox_bar = reinterpret_cast<u64 *>(s_len + kMaxBatches);   // [2]
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
             const int item = p.order[(int64_t)global_batch(idx / TM) * TM + idx % TM];
             s_item[idx] = item;
             s_frames[idx] = item >= 0 ? p.frames[item] : 0;
+            s_row[idx] = item >= 0 ? p.item_row[item] : 0;
         }
         __syncthreads();
         if (tid < batches) s_len[tid] = s_frames[tid * TM];    // longest first
@@ -272,10 +274,10 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
                 const int item = s_item[b * TM + r];
                 float *dst0 = p.score0 + ((int64_t)global_batch(b) * TM + r) * LDP + c;
                 if (item >= 0 && c < S) {
-                    const float v = convert_observation<kFlags>(load_observation(p.observation, (int64_t)item * p.T * S + c, p.obs_dtype)) +
-                                    p.initial[c];
+                    const int64_t e0 = s_row[b * TM + r] * S + c;
+                    const float v = convert_observation<kFlags>(load_observation(p.observation, e0, p.obs_dtype)) + p.initial[c];
                     *dst0 = v;
-                    p.history[(int64_t)item * p.T * S + c] = v;
+                    p.history[e0] = v;
                 } else {
                     dst0[0] = 0.f;                               // padding stays finite, in both buffers
                     dst0[p.score_stride] = 0.f;
@@ -328,10 +330,11 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
             // emission of the cells this thread finalises, fetched now and used after the K loop
             float4 emit = make_float4(0.f, 0.f, 0.f, 0.f);
             const int fin_item = mine ? s_item[b * TM + fin_row] : -1;
+            const int64_t fin_row0 = mine ? s_row[b * TM + fin_row] : 0;
             const bool fin_live = mine && fin_item >= 0 && tau < s_frames[b * TM + fin_row] && j0 + fin_col < S;
             if (fin_live) {
                 if (p.frames_ready) wait_for_frame(tau);
-                const int64_t e0 = ((int64_t)fin_item * p.T + tau) * S + j0 + fin_col;
+                const int64_t e0 = (fin_row0 + tau) * S + j0 + fin_col;
                 if (obs_vec) {
                     emit = __ldcg(reinterpret_cast<const float4 *>(p.observation + e0));
                 } else {
@@ -432,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
                         v.z = convert_observation<kFlags>(emit.z) + m.z;
                         v.w = convert_observation<kFlags>(emit.w) + m.w;
                         float *dst = p.score0 + (tau & 1) * p.score_stride + (row0 + fin_row) * LDP + col0;
-                        float *hist = p.history + ((int64_t)fin_item * p.T + tau) * S + col0;
+                        float *hist = p.history + (fin_row0 + tau) * S + col0;
                         if (col0 + 3 < S) {
                             *reinterpret_cast<float4 *>(dst) = v;
                             if (hist_vec) __stcs(reinterpret_cast<float4 *>(hist), v);
@@ -557,6 +560,7 @@ cudaError_t launch_forward_cluster(const ForwardArgs &a, cudaStream_t stream) {
     p.transition = a.ws.transition_pad;
     p.initial = a.initial;
     p.frames = a.ws.frames;
+    p.item_row = a.ws.item_row;
     p.order = a.ws.order;
     p.score0 = a.ws.score[0];
     p.score_stride = a.ws.score[1] - a.ws.score[0];
@@ -565,7 +569,6 @@ cudaError_t launch_forward_cluster(const ForwardArgs &a, cudaStream_t stream) {
     p.final_state = a.ws.final_state;
     p.sync = a.ws.sync;
     p.frames_ready = a.frames_ready;
-    p.T = a.T;
     p.S = (int)a.S;
     p.LDP = (int)padded_sources(a.S);
     p.NJT = cluster_njt(a.S);

@@ -78,7 +78,7 @@ template <typename Shape>
 size_t smem_bytes(int ldp) {
     return sizeof(float) * (ring_floats<Shape>() + kTileCells + kWarps * kTileCells +
                             (Shape::kResident ? Shape::TN * (ldp + 4) : 0)) +
-           sizeof(int) * 2 * Shape::TM + sizeof(u64) * 2 * Shape::NSTAGE;
+           sizeof(int) * 4 * Shape::TM + sizeof(u64) * 2 * Shape::NSTAGE;
 }
 
 __device__ __forceinline__ u64 add2(u64 a, u64 b) {     // two fp32 adds (FADD2), IEEE rn
@@ -137,20 +137,20 @@ __device__ __forceinline__ void group_wait(const unsigned *counter, unsigned tar
 #endif
 
 struct SplitParams {
-    const float *observation;   // (B,T,S); 2-byte elements when obs_dtype != 0
+    const float *observation;   // (rows,S), item b at rows item_row[b] ..; 2-byte elements when obs_dtype != 0
     int obs_dtype;              // 0 fp32, 1 fp16, 2 bf16
     const float *transition;    // padded copy (SJ, LDP), -inf outside (S,S)
     const float *initial;       // (S,)
     const int32_t *frames;      // (B,)
+    const int64_t *item_row;    // (B,) first row of each item in observation / history
     const int32_t *order;       // (Bpad,) items longest first, -1 = empty slot
     float *score0;              // 3 rotating buffers (Bpad, LDP), `score_stride` floats apart
     int64_t score_stride;
-    float *history;             // (B,T,S) fp32: every P_t
+    float *history;             // (rows,S) fp32: every P_t
     float *posterior;           // (B,S) or null
     int32_t *final_state;       // (B,)
     unsigned *sync;             // per group: barrier counter (+0), current batch (+1); queue head after the groups
     const int32_t *frames_ready;
-    int64_t T;
     int S, LDP, NJT, NG, num_batches;
 };
 
@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(kThreads, 1) forward_split_kernel(const SplitP
     float *partial = tile + TM * TN;                            // [warp][TM][TN] per-warp maxima
     float *A_res = partial + kWarps * TM * TN;                  // resident shape: [TN][LDP + 4] transition block
     const int LDA = p.LDP + 4;                                  // rows 4 banks apart, like the ring's
-    int *slot_item = reinterpret_cast<int *>(A_res + (Shape::kResident ? TN * LDA : 0));
+    int64_t *slot_row = reinterpret_cast<int64_t *>(A_res + (Shape::kResident ? TN * LDA : 0));   // [TM] first row of the slot's item
+    int *slot_item = reinterpret_cast<int *>(slot_row + TM);
     int *slot_frames = slot_item + TM;
     u64 *full_bar = reinterpret_cast<u64 *>(slot_frames + TM);  // [NSTAGE] one arrival per thread: its copies landed
     u64 *empty_bar = full_bar + NSTAGE;                         // [NSTAGE] one arrival per warp: done reading
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_split_kernel(const SplitP
             const int item = p.order[row0 + tid];
             slot_item[tid] = item;
             slot_frames[tid] = item >= 0 ? p.frames[item] : 0;
+            slot_row[tid] = item >= 0 ? p.item_row[item] : 0;
         }
         __syncthreads();
         const int batch_frames = slot_frames[0];        // longest first
@@ -279,12 +281,12 @@ __global__ void __launch_bounds__(kThreads, 1) forward_split_kernel(const SplitP
                 float *dst0 = p.score0 + (row0 + r) * LDP;
                 float *dst1 = dst0 + p.score_stride;
                 float *dst2 = dst1 + p.score_stride;
-                const int64_t obs0 = (int64_t)max(item, 0) * p.T * S;
+                const int64_t obs0 = slot_row[r] * S;
                 for (int c = j0 + lane; c < c_end; c += kWarp) {
                     if (item >= 0 && c < S) {
                         const float v = convert_observation<kFlags>(load_observation(p.observation, obs0 + c, p.obs_dtype)) + p.initial[c];
                         dst0[c] = v;
-                        p.history[(int64_t)item * p.T * S + c] = v;
+                        p.history[obs0 + c] = v;
                     } else {
                         dst0[c] = 0.f;                   // padding stays finite, in all buffers
                         dst1[c] = 0.f;
@@ -307,11 +309,11 @@ __global__ void __launch_bounds__(kThreads, 1) forward_split_kernel(const SplitP
                     const int r = tid / (TN / 4), c4 = tid % (TN / 4);
                     const int item = slot_item[r];
                     if (item >= 0 && t < slot_frames[r] && j0 + c4 * 4 < S)
-                        cp_async16(tile + r * TN + c4 * 4, p.observation + ((int64_t)item * p.T + t) * S + j0 + c4 * 4);
+                        cp_async16(tile + r * TN + c4 * 4, p.observation + (slot_row[r] + t) * S + j0 + c4 * 4);
                 }
             } else {
                 load_emission_tile_plain<TM, TN, kThreads>(tile, p.observation, p.obs_dtype, slot_item, slot_frames,
-                                                           p.T, S, t, j0);
+                                                           slot_row, S, t, j0);
             }
             for (int s = 0; s < ahead; ++s)
                 load_stage_A<Shape>(ring + ((slot + s) % NSTAGE) * kStageFloats + ld_smem, ld_A + s * KS, ld_stride10);
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_split_kernel(const SplitP
                 if (col < S && slot_item[r] >= 0) {                       // padding never changes
                     const int64_t off = (row0 + r) * LDP + col;
                     const bool live = t < slot_frames[r];
-                    float *hist = live ? p.history + ((int64_t)slot_item[r] * p.T + t) * S + col : nullptr;
+                    float *hist = live ? p.history + (slot_row[r] + t) * S + col : nullptr;
                     if (col + 3 < S) {
                         const float4 v = live ? *reinterpret_cast<const float4 *>(tile + r * TN + c4 * 4)
                                               : __ldcg(reinterpret_cast<const float4 *>(P_cur + off));
@@ -568,6 +570,7 @@ static cudaError_t launch_split_t(const ForwardArgs &a, cudaStream_t stream) {
     p.transition = a.ws.transition_pad;
     p.initial = a.initial;
     p.frames = a.ws.frames;
+    p.item_row = a.ws.item_row;
     p.order = a.ws.order;
     p.score0 = a.ws.score[0];
     p.score_stride = a.ws.score[1] - a.ws.score[0];
@@ -576,7 +579,6 @@ static cudaError_t launch_split_t(const ForwardArgs &a, cudaStream_t stream) {
     p.final_state = a.ws.final_state;
     p.sync = a.ws.sync;
     p.frames_ready = a.frames_ready;
-    p.T = a.T;
     p.S = (int)a.S;
     p.LDP = (int)padded_sources(a.S);
     p.NJT = (int)((a.S + Shape::TN - 1) / Shape::TN);

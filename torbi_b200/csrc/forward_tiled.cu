@@ -79,7 +79,7 @@ constexpr int stage_floats(int M) { return (tile_rows(M) + TN) * LDS_; }
 constexpr size_t smem_bytes(int M) {
     return sizeof(float) * (NSTAGE * stage_floats(M) + 2 * tile_rows(M) * TN)  // ring + emission/score + max tiles
            + sizeof(uint16_t) * tile_rows(M) * TN                              // winning chunk -> backpointer tile
-           + sizeof(int) * 4 * tile_rows(M)                                    // per-slot item id, length; banded: outside max / index
+           + sizeof(int) * 6 * tile_rows(M)                                    // per-slot item id, length, first row (int64); banded: outside max / index
            + sizeof(u64) * 2 * NSTAGE;                                         // full / empty mbarrier per ring slot
 }
 static_assert(smem_bytes(4) <= 227 * 1024, "shared memory budget");
@@ -133,16 +133,17 @@ __device__ __forceinline__ void group_wait(const unsigned *counter, unsigned tar
 }
 
 struct TiledParams {
-    const float *observation;   // (B,T,S); 2-byte elements when obs_dtype != 0
+    const float *observation;   // (rows,S), item b at rows item_row[b] ..; 2-byte elements when obs_dtype != 0
     int obs_dtype;              // 0 fp32, 1 fp16, 2 bf16
     const float *transition;    // padded copy (SJ, LDP), -inf outside (S,S)
     const float *initial;       // (S,)
     const int32_t *frames;      // (B,)
+    const int64_t *item_row;    // (B,) first row of each item in observation / history / backptr
     const int32_t *order;       // (Bpad,) items longest first, -1 = empty slot
     float *score0;              // 3 rotating buffers (Bpad, LDP), `score_stride` floats apart;
     int64_t score_stride;       // row = position in `order`
-    uint16_t *backptr;          // (B,T,S)
-    float *history;             // score-history mode: (B,T,S) fp32, every P_t (same memory as backptr)
+    uint16_t *backptr;          // (rows,S)
+    float *history;             // score-history mode: (rows,S) fp32, every P_t (same memory as backptr)
     float *posterior;           // (B,S) or null
     int32_t *final_state;       // (B,)
     unsigned *sync;             // per group: barrier counter (+0) and current batch (+1); queue head at [0] of the last line
@@ -151,7 +152,6 @@ struct TiledParams {
     int64_t block_stride;         // 16-state block of the corresponding score row; `block_stride` floats apart
     const unsigned *band;         // banded mode: per destination tile S - first / last+1 source differing from `outside`
     const float *outside;         // banded mode: the value every transition entry outside the windows has
-    int64_t T;
     int S, LDP, NJT, NG, num_batches;
 };
 
@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
     // Ring synchronisation without CTA-wide barriers: full[slot] collects one arrival per thread
     // once its async copies for the stage have landed; empty[slot] one per warp once it has
     // finished reading the stage.  Warps may drift apart by up to a stage.
-    u64 *full_bar = reinterpret_cast<u64 *>(out_i + TM);               // [NSTAGE]
+    int64_t *slot_row = reinterpret_cast<int64_t *>(out_i + TM);       // [TM] first row of the slot's item
+    u64 *full_bar = reinterpret_cast<u64 *>(slot_row + TM);            // [NSTAGE]
     u64 *empty_bar = full_bar + NSTAGE;                                // [NSTAGE]
     if (threadIdx.x == 0) {
         for (int k = 0; k < NSTAGE; ++k) {
@@ -376,6 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             const int item = p.order[row0 + tid];
             slot_item[tid] = item;
             slot_frames[tid] = item >= 0 ? p.frames[item] : 0;
+            slot_row[tid] = item >= 0 ? p.item_row[item] : 0;
         }
         __syncthreads();
         const int batch_frames = slot_frames[0];        // longest first
@@ -389,12 +391,12 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                 float *dst0 = p.score0 + (row0 + r) * LDP;
                 float *dst1 = dst0 + p.score_stride;
                 float *dst2 = dst1 + p.score_stride;
-                const int64_t obs0 = (int64_t)max(item, 0) * p.T * S;
+                const int64_t obs0 = slot_row[r] * S;
                 for (int c = j0 + lane; c < c_end; c += kWarp) {
                     if (item >= 0 && c < S) {
                         const float v = convert_observation<kFlags>(load_observation(p.observation, obs0 + c, p.obs_dtype)) + p.initial[c];
                         dst0[c] = v;
-                        if (kHist) p.history[(int64_t)item * p.T * S + c] = v;
+                        if (kHist) p.history[obs0 + c] = v;
                     } else {
                         dst0[c] = 0.f;                   // padding stays finite, in all buffers
                         dst1[c] = 0.f;
@@ -432,11 +434,11 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                     const int item = slot_item[r];
                     if (item >= 0 && t < slot_frames[r] && j0 + c4 * 4 < S)
                         cp_async16(tile + r * TN + c4 * 4,
-                                   p.observation + ((int64_t)item * p.T + t) * S + j0 + c4 * 4);
+                                   p.observation + (slot_row[r] + t) * S + j0 + c4 * 4);
                 }
             } else {
                 load_emission_tile_plain<TM, TN, kThreads>(tile, p.observation, p.obs_dtype, slot_item, slot_frames,
-                                                           p.T, S, t, j0);
+                                                           slot_row, S, t, j0);
             }
             // (stage_counter already points at the first stage of step t: the previous step is done)
             if (nstages > 0) load_stage_A<TM>(ring + (stage_counter % NSTAGE) * kStageFloats + ld_smem, ld_A, ld_stride10);
@@ -664,7 +666,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                     const int64_t off = (row0 + r) * LDP + col;
                     const bool live = t < slot_frames[r];
                     // score-history mode: P_t of live rows also goes to the (B,T,S) history (streaming store)
-                    float *hist = (kHist && live) ? p.history + ((int64_t)slot_item[r] * p.T + t) * S + col : nullptr;
+                    float *hist = (kHist && live) ? p.history + (slot_row[r] + t) * S + col : nullptr;
                     if (col + 3 < S) {
                         v = live ? *reinterpret_cast<const float4 *>(tile + r * TN + c4 * 4)
                                  : __ldcg(reinterpret_cast<const float4 *>(P_cur + off));
@@ -719,14 +721,14 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                 for (int idx = tid; idx < TM * (TN / 8); idx += kThreads) {
                     const int r = idx / (TN / 8), c8 = idx % (TN / 8);
                     if (t < slot_frames[r] && j0 + c8 * 8 < S)
-                        *reinterpret_cast<uint4 *>(p.backptr + ((int64_t)slot_item[r] * p.T + t) * S + j0 + c8 * 8) =
+                        *reinterpret_cast<uint4 *>(p.backptr + (slot_row[r] + t) * S + j0 + c8 * 8) =
                             *reinterpret_cast<const uint4 *>(bp_tile + r * TN + c8 * 8);
                 }
             } else {
                 for (int idx = tid; idx < TM * TN; idx += kThreads) {
                     const int r = idx / TN, c = idx % TN;
                     if (t < slot_frames[r] && j0 + c < S)
-                        p.backptr[((int64_t)slot_item[r] * p.T + t) * S + j0 + c] = bp_tile[idx];
+                        p.backptr[(slot_row[r] + t) * S + j0 + c] = bp_tile[idx];
                 }
             }
             }   // !kHist
@@ -828,6 +830,7 @@ static cudaError_t launch_tiled_t(const ForwardArgs &a, cudaStream_t stream) {
     p.transition = a.ws.transition_pad;
     p.initial = a.initial;
     p.frames = a.ws.frames;
+    p.item_row = a.ws.item_row;
     p.order = a.ws.order;
     p.score0 = a.ws.score[0];
     p.score_stride = a.ws.score[1] - a.ws.score[0];
@@ -839,7 +842,6 @@ static cudaError_t launch_tiled_t(const ForwardArgs &a, cudaStream_t stream) {
     p.final_state = a.ws.final_state;
     p.sync = a.ws.sync;
     p.frames_ready = a.frames_ready;
-    p.T = a.T;
     p.S = (int)a.S;
     p.LDP = (int)tiled_ldp(a.S);
     const int SJ = (int)tiled_sj(a.S);

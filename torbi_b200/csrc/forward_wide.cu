@@ -30,22 +30,22 @@ constexpr int kWideThreads = 512;
 constexpr int kWideWarps = kWideThreads / kWarp;
 
 struct WideParams {
-    const float *observation;   // (B,T,S); 2-byte elements when obs_dtype != 0
+    const float *observation;   // (rows,S), item b at rows item_row[b] ..; 2-byte elements when obs_dtype != 0
     int obs_dtype;              // 0 fp32, 1 fp16, 2 bf16
     float *checkpoints;         // (B, ck_rows, S) or null: P_t for t = k * checkpoint_every
     int64_t checkpoint_every, ck_rows;
     const float *transition;    // padded copy (SJ, LDP), -inf outside (S,S)
     const float *initial;       // (S,)
     const int32_t *frames;      // (B,)
+    const int64_t *item_row;    // (B,) first row of each item in observation / backptr
     const int32_t *order;       // (Bpad,) items longest first
     float *score0;              // 2 alternating buffers (Bpad, LDP), `score_stride` floats apart
     int64_t score_stride;
-    uint16_t *backptr;          // (B,T,S)
+    uint16_t *backptr;          // (rows,S)
     float *posterior;           // (B,S) or null
     int32_t *final_state;       // (B,)
     unsigned *sync;             // grid barrier counter
     const int32_t *frames_ready;
-    int64_t T;
     int B, S, LDP, NC, R;
     int resident_rows;          // leading rows of each CTA's transition slice kept in shared memory
 };
@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
     float *Ps = smem;                                    // [BC][LDP] previous scores
     float *As = smem + BC * LDP;                         // [resident_rows][LDP] transition slice
     __shared__ int slot_item[BC], slot_frames[BC];
+    __shared__ int64_t slot_row[BC];
     __shared__ int ready_shared;
 
     const int tid = threadIdx.x, lane = tid % kWarp, warp = tid / kWarp;
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
             const int item = tid < nb ? p.order[first + tid] : -1;
             slot_item[tid] = item;
             slot_frames[tid] = item >= 0 ? p.frames[item] : 0;
+            slot_row[tid] = item >= 0 ? p.item_row[item] : 0;
         }
         __syncthreads();
         const int group_frames = slot_frames[0];         // longest first
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
             for (int b = warp; b < nb; b += kWideWarps) {
                 const int item = slot_item[b];
                 float *dst0 = p.score0 + (int64_t)(first + b) * LDP;
-                const int64_t obs0 = (int64_t)item * p.T * S;
+                const int64_t obs0 = slot_row[b] * S;
                 for (int c = j_begin + lane; c < c_end; c += kWarp) {
                     if (c < S) {
                         dst0[c] = convert_observation<kFlags>(load_observation(p.observation, obs0 + c, p.obs_dtype)) + p.initial[c];
@@ -162,9 +164,8 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
                 // emissions (and carried scores of finished sequences) fetched early by lane b
                 float emit = 0.f;
                 if (lane < nbw) {
-                    const int item = slot_item[b0 + lane];
                     emit = t < slot_frames[b0 + lane]
-                        ? convert_observation<kFlags>(load_observation(p.observation, ((int64_t)item * p.T + t) * S + j, p.obs_dtype))
+                        ? convert_observation<kFlags>(load_observation(p.observation, (slot_row[b0 + lane] + t) * S + j, p.obs_dtype))
                         : __ldcg(P_cur + (int64_t)(b0 + lane) * LDP + j);
                 }
                 float best[BW];
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
                         const bool live = t < slot_frames[bb];
                         P_new[(int64_t)bb * LDP + j] = live ? e + v : e;         // viterbi.cpp:102 / carried
                         if (live) {
-                            p.backptr[((int64_t)slot_item[bb] * p.T + t) * S + j] = (uint16_t)min(arg, S - 1);
+                            p.backptr[(slot_row[bb] + t) * S + j] = (uint16_t)min(arg, S - 1);
                             if (p.checkpoints && t % p.checkpoint_every == 0)
                                 p.checkpoints[((int64_t)slot_item[bb] * p.ck_rows + (t / p.checkpoint_every - 1)) * S + j] = e + v;
                         }
@@ -342,6 +343,7 @@ cudaError_t launch_forward_wide(const ForwardArgs &a, cudaStream_t stream) {
     p.transition = a.ws.transition_pad;
     p.initial = a.initial;
     p.frames = a.ws.frames;
+    p.item_row = a.ws.item_row;
     p.order = a.ws.order;
     p.score0 = a.ws.score[0];
     p.score_stride = a.ws.score[1] - a.ws.score[0];
@@ -350,7 +352,6 @@ cudaError_t launch_forward_wide(const ForwardArgs &a, cudaStream_t stream) {
     p.final_state = a.ws.final_state;
     p.sync = a.ws.sync;
     p.frames_ready = a.frames_ready;
-    p.T = a.T;
     p.B = (int)a.B;
     p.S = (int)a.S;
     p.LDP = (int)padded_sources(a.S);

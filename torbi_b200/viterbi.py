@@ -172,3 +172,92 @@ def decode_host(
             devices.data_ptr(), devices.numel())
     _ffi.check(status)
     return (out, posterior) if return_posterior else out
+
+
+def _packed_arguments(observation, item_row, batch_frames, transition, initial):
+    if observation.dim() != 2:
+        raise ValueError(f'observation must have shape (rows, states), got {tuple(observation.shape)}')
+    rows, states = observation.shape
+    _check_inputs(observation[None], transition, initial)
+    frames = batch_frames.detach().to(device='cpu', dtype=torch.int32).contiguous()
+    first = torch.as_tensor(item_row).detach().to(device='cpu', dtype=torch.int64).contiguous()
+    if frames.dim() != 1 or first.shape != frames.shape:
+        raise ValueError('item_row and batch_frames must be 1-D and of equal length')
+    return rows, states, first, frames
+
+
+def decode_packed(
+    observation: torch.Tensor,
+    item_row: torch.Tensor,
+    batch_frames: torch.Tensor,
+    transition: torch.Tensor,
+    initial: torch.Tensor,
+    *,
+    flags: int = 0,
+    return_posterior: bool = False,
+    out: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """Decode a PACKED batch (torbi_b200_decode_packed): `observation` is one (rows, S) CUDA
+    buffer, item b is its rows item_row[b] .. item_row[b] + batch_frames[b]; returns (rows,)
+    int32 with every item's states in its own rows.  No padding to the longest item
+    (the reference pads, data/collate.py:26-31) -- the pieces of a chunked sequence or the
+    files of a batch are decoded where they lie."""
+    rows, states, first, frames = _packed_arguments(observation, item_row, batch_frames, transition, initial)
+    if observation.device.type != 'cuda':
+        raise RuntimeError('torbi_b200.decode_packed needs CUDA tensors (decode_host_packed takes host buffers)')
+    device = observation.device
+    if transition.device != device or initial.device != device:
+        raise RuntimeError('observation, transition and initial must be on the same device')
+    lib = _ffi.library()
+    observation, transition, initial = observation.contiguous(), transition.contiguous(), initial.contiguous()
+    flags |= _OBS_FLAGS[observation.dtype]
+    batch = frames.numel()
+    with torch.cuda.device(device):
+        if out is None:
+            out = torch.zeros((rows,), dtype=torch.int32, device=device)
+        elif out.dtype != torch.int32 or tuple(out.shape) != (rows,) or not out.is_contiguous() or out.device != device:
+            raise ValueError('out must be a contiguous int32 tensor of shape (rows,) on the device of observation')
+        posterior = torch.empty((batch, states), dtype=torch.float32, device=device) if return_posterior else None
+        workspace_bytes = lib.torbi_b200_workspace_bytes_packed(
+            first.data_ptr(), frames.data_ptr(), batch, rows, states, flags, _sm_count(device))
+        if workspace_bytes == 0:
+            _ffi.check(_ffi.ERR_INVALID_ARGUMENT)
+        workspace = torch.empty(workspace_bytes, dtype=torch.uint8, device=device)
+        _ffi.check(lib.torbi_b200_decode_packed(
+            observation.data_ptr(), first.data_ptr(), frames.data_ptr(), transition.data_ptr(), initial.data_ptr(),
+            batch, rows, states, flags, out.data_ptr(), posterior.data_ptr() if return_posterior else None,
+            workspace.data_ptr(), workspace_bytes, torch.cuda.current_stream(device).cuda_stream))
+    return (out, posterior) if return_posterior else out
+
+
+def decode_host_packed(
+    observation: torch.Tensor,
+    item_row: torch.Tensor,
+    batch_frames: torch.Tensor,
+    transition: torch.Tensor,
+    initial: torch.Tensor,
+    gpu: int = 0,
+    *,
+    flags: int = 0,
+    return_posterior: bool = False,
+    out: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """decode_packed for HOST tensors (torbi_b200_decode_host_packed): copies, decode and the copy
+    back of the (rows,) indices inside the C call."""
+    rows, states, first, frames = _packed_arguments(observation, item_row, batch_frames, transition, initial)
+    for name, tensor in (('observation', observation), ('transition', transition), ('initial', initial)):
+        if tensor.device.type != 'cpu':
+            raise RuntimeError(f'decode_host_packed: {name} must be a CPU tensor')
+    lib = _ffi.library()
+    observation, transition, initial = observation.contiguous(), transition.contiguous(), initial.contiguous()
+    flags |= _OBS_FLAGS[observation.dtype]
+    batch = frames.numel()
+    if out is None:
+        out = torch.zeros((rows,), dtype=torch.int32)
+    elif out.dtype != torch.int32 or tuple(out.shape) != (rows,) or not out.is_contiguous() or out.device.type != 'cpu':
+        raise ValueError('out must be a contiguous CPU int32 tensor of shape (rows,)')
+    posterior = torch.empty((batch, states), dtype=torch.float32) if return_posterior else None
+    _ffi.check(lib.torbi_b200_decode_host_packed(
+        observation.data_ptr(), first.data_ptr(), frames.data_ptr(), transition.data_ptr(), initial.data_ptr(),
+        batch, rows, states, flags, out.data_ptr(), posterior.data_ptr() if return_posterior else None, gpu))
+    return (out, posterior) if return_posterior else out
