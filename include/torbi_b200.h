@@ -228,6 +228,24 @@ TORBI_B200_API int torbi_b200_decode_host_multi(const void *observation, const i
                                  uint32_t flags, int32_t *indices, float *posterior,
                                  const int *devices, int n_devices);
 
+/*
+ * Framewise normalised entropy for the chunked long-sequence mode -- replaces `entropy` of
+ * /root/reference/torbi/chunk.py:81-85 (torch CPU ops over the whole (states, frames) transpose):
+ *     H[t] = -( sum_s exp(x[t][s]) * x[t][s] ) / log(states)
+ * on the observation exactly as stored (the reference's Dataset chunks before any conversion,
+ * data/dataset.py:21-23).  One pass over HBM, one warp per frame, fixed summation order.
+ *
+ *   observation  device (rows, states) fp32 (fp16 / bf16 with TORBI_B200_OBS_F16 / _BF16 in `flags`)
+ *   entropy      device (rows, 2) fp32, output: [t][0] = H[t]; [t][1] = sum_s |exp(x) x| / log(states),
+ *                the magnitude that bounds the rounding difference to any other fp32 summation order
+ *                (|H - H'| <= ~2 states 2^-24 [t][1]): a caller that must reproduce the reference's
+ *                split decisions re-evaluates only the frames whose H is that close to the threshold
+ *                (torbi_b200/chunk.py does, with the reference's own ops).
+ * Enqueued on `stream` on the current device; does not synchronise.
+ */
+TORBI_B200_API int torbi_b200_entropy(const void *observation, int64_t rows, int64_t states, uint32_t flags,
+                                      float *entropy, void *stream);
+
 /* Free the host-entry arenas (all devices).  Safe to call at any time no decode
  * is in flight. */
 TORBI_B200_API void torbi_b200_release(void);

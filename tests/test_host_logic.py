@@ -175,6 +175,41 @@ def test_chunk_matches_reference_golden(name, golden):
         assert all(c.data_ptr() == x[b].data_ptr() for c, b in zip(chunks, [0] + expected))   # views
 
 
+def test_evaluation_runner_host_logic(tmp_path, monkeypatch):
+    """evaluate.datasets (evaluate/core.py:14-123) with the decode stubbed out: corpus synthesis,
+    partition bookkeeping, the un-chunked reference decode, RPA and real-time-factor reporting."""
+    import json
+    calls = []
+
+    def fake_from_files_to_files(input_files, output_files, transition_file=None, initial_file=None,
+                                 log_probs=False, gpu=None, num_threads=None):
+        assert log_probs and torch.load(transition_file).shape == (1440, 1440)
+        calls.append(torbi_b200.MIN_CHUNK_SIZE)
+        with torbi_b200.timing.context('torbi'):
+            for source, target in zip(input_files, output_files):
+                bins = torch.load(source).argmax(dim=-1).to(torch.int32)
+                if torbi_b200.MIN_CHUNK_SIZE is not None:
+                    bins[::7] += 1                                  # the "chunked" decode differs a little
+                torch.save(bins, target)
+    monkeypatch.setattr(torbi_b200, 'from_files_to_files', fake_from_files_to_files)
+    stems = torbi_b200.evaluate.synthetic_dataset('tiny', tmp_path, files=3, states=1440, median_frames=60)
+    assert json.loads((tmp_path / 'assets' / 'partitions' / 'tiny.json').read_text()) == stems
+    x = torch.load(tmp_path / 'data' / 'cache' / 'tiny' / f'{stems[0]}.pt')
+    assert x.dim() == 2 and x.shape[1] == 1440 and torch.allclose(x.exp().sum(-1), torch.ones(x.shape[0]), atol=1e-4)
+    result = torbi_b200.evaluate.datasets(['tiny'], gpu=0, root=tmp_path)
+    assert calls == [None] and result['tiny']['rpa'] == {'0': 1.0, '1': 1.0, '2': 1.0}      # CONFIG = torbi: against itself
+    assert set(result['tiny']['rtf']) == {'torbi', 'end_to_end'} and result['tiny']['files'] == 3
+    assert result['tiny']['rpa_vs_truth']['2'] > 0.5
+    monkeypatch.setattr(torbi_b200, 'CONFIG', 'chunked')
+    monkeypatch.setattr(torbi_b200, 'MIN_CHUNK_SIZE', 32)
+    result = torbi_b200.evaluate.datasets(['tiny'], gpu=0, root=tmp_path)
+    assert calls == [None, 32]                                                                  # reference outputs reused
+    assert 0.8 < result['tiny']['rpa']['0'] < 0.9 and result['tiny']['rpa']['1'] == 1.0
+    assert json.loads((tmp_path / 'eval' / 'chunked.json').read_text())['tiny']['frames'] == result['tiny']['frames']
+    from torbi_b200.evaluate.__main__ import parse_args
+    assert parse_args(['--datasets', 'a', 'b', '--gpu', '0'])['datasets'] == ['a', 'b']
+
+
 def test_cli_and_configure(tmp_path):
     from torbi_b200.__main__ import parse_args
     args = parse_args(['--input_files', 'a.pt', 'b.pt', '--output_files', 'c.pt', 'd.pt',
@@ -409,6 +444,26 @@ def test_native_reader_keeps_half_precision_files(tmp_path, dtype):
     assert native.load_batch(files, threads=2) is None
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_native_reader_packs_a_batch_without_padding(tmp_path, dtype):
+    from torbi_b200.data import native
+    g = torch.Generator().manual_seed(4)
+    tensors = [torch.randn(n, 12, generator=g).to(dtype) for n in (5, 9, 1, 9)]
+    files = []
+    for i, tensor in enumerate(tensors):
+        files.append(tmp_path / f'{i}.pt')
+        torch.save(tensor, files[-1])
+    for out in (None, torch.full((1000,), float('nan'))):
+        observation, item_row, frames = native.load_batch_packed(files, threads=2, out=out)
+        assert observation.dtype == dtype and observation.shape == (24, 12)
+        assert item_row.tolist() == [0, 5, 14, 15] and frames.tolist() == [5, 9, 1, 9]
+        assert torch.equal(observation, torch.cat(tensors))
+    torch.save(torch.randn(3, 11), files[1])                       # another width: generic path
+    assert native.load_batch_packed(files, threads=2) is None
+    assert torbi_b200.core.size_capped_batches([10, 50, 20, 40, 30], 3, max_bytes=90) == [[1, 3], [4, 2, 0]]
+    assert torbi_b200.core.size_capped_batches([500, 5], 8, max_bytes=90) == [[0], [1]]
+
+
 def test_file_pipeline_stops_its_loader_when_the_decode_fails(tmp_path, monkeypatch):
     """A failing decode must not leave the loader thread blocked on its queue holding pinned buffers."""
     import threading
@@ -422,6 +477,7 @@ def test_file_pipeline_stops_its_loader_when_the_decode_fails(tmp_path, monkeypa
     def boom(**kwargs):
         raise RuntimeError('decode failed')
     monkeypatch.setattr(core, 'from_probabilities', boom)
+    monkeypatch.setattr(core, '_from_probabilities_packed', lambda *args, **kwargs: boom())
     before = threading.active_count()
     with pytest.raises(RuntimeError, match='decode failed'):
         core._from_files_native(files, [100] * len(files), {f: f + '.out' for f in files}, None, None, True, 0,

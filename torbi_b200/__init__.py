@@ -37,6 +37,7 @@ def configure(config_file):
 ###############################################################################
 
 from . import _ffi                                   # noqa: E402
+from . import timing                                 # noqa: E402
 from .viterbi import decode, decode_host, decode_packed, decode_host_packed   # noqa: E402
 from .core import *                                  # noqa: E402,F401,F403
 from .core import lpt_shards, size_bucketed_batches  # noqa: E402,F401

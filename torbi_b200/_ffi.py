@@ -60,6 +60,7 @@ SIGNATURES = {
         _p, _p, _p, _p, _i64, _i64, _i64, ctypes.c_uint32, _p, _p, ctypes.c_int]),
     'torbi_b200_decode_host_multi': (ctypes.c_int, [
         _p, _p, _p, _p, _i64, _i64, _i64, ctypes.c_uint32, _p, _p, _p, ctypes.c_int]),
+    'torbi_b200_entropy': (ctypes.c_int, [_p, _i64, _i64, ctypes.c_uint32, _p, _p]),
     'torbi_b200_release': (None, []),
     'torbi_b200_launch_count': (ctypes.c_uint64, []),
     'torbi_b200_last_kernel': (ctypes.c_char_p, []),

@@ -1,7 +1,7 @@
 """Decode-relevant configuration constants, same names and defaults as
 /root/reference/torbi/config/defaults.py (lines cited per constant).  The
-evaluation / dataset bookkeeping constants of that file are out of scope
-(SURVEY.md section 8).  Override with `torbi_b200.configure(path)` or the CLI's
+dataset download / partition bookkeeping constants of that file are out of scope
+(SURVEY.md section 8); the evaluation runner takes its directories from `root`.  Override with `torbi_b200.configure(path)` or the CLI's
 `--config path.py` (the reference does this through yapecs,
 /root/reference/torbi/__init__.py:10-11)."""
 
@@ -24,3 +24,10 @@ BATCH_SIZE = 512
 
 # Number of parallel CPU workers (defaults.py:83)
 NUM_WORKERS = 0
+
+# Datasets evaluated by `python -m torbi_b200.evaluate` (defaults.py:56 lists daps / vctk, which need
+# downloads; the synthetic corpus stands in)
+DATASETS = ['synthetic']
+
+# Thresholds (in number of 5 cent bins) for raw pitch accuracy (defaults.py:62)
+PITCH_ERROR_THRESHOLDS = [0, 1, 2]

@@ -22,8 +22,8 @@ from typing import Dict, List, Optional, Sequence, Union
 import torch
 
 import torbi_b200
-from . import _ffi
-from .viterbi import decode
+from . import _ffi, timing
+from .viterbi import decode, decode_packed
 
 __all__ = [
     'from_probabilities', 'from_file', 'from_file_to_file', 'from_files_to_files',
@@ -73,6 +73,23 @@ def lpt_shards(costs: Sequence[int], shards: int) -> List[List[int]]:
         bins[k].append(item)
         load[k] += int(costs[item])
     return [sorted(b) for b in bins]
+
+
+def size_capped_batches(sizes: Sequence[int], batch_size: int, max_bytes: int = 1 << 29) -> List[List[int]]:
+    """Batches of file indices, largest files first, at most `batch_size` files and at most
+    `max_bytes` in total (a single larger file makes a batch of its own): the batching of the packed
+    (unpadded) layout, where a batch costs the sum of its files rather than count x longest."""
+    order = sorted(range(len(sizes)), key=lambda i: -int(sizes[i]))
+    batches: List[List[int]] = []
+    total = 0
+    for i in order:
+        if batches and len(batches[-1]) < batch_size and total + int(sizes[i]) <= max_bytes:
+            batches[-1].append(i)
+            total += int(sizes[i])
+        else:
+            batches.append([i])
+            total = int(sizes[i])
+    return batches
 
 
 def size_bucketed_batches(sizes: Sequence[int], batch_size: int,
@@ -146,6 +163,78 @@ def _is_banded(transition: torch.Tensor) -> bool:
     return bool((as_bits != as_bits[0, -1]).float().mean() < 0.35)
 
 
+def _prepare_model(states, batch, transition, initial, log_probs, device, banded):
+    """Defaults and log-space conversion of `initial` / `transition` (core.py:161-186) -> fp32 tensors on
+    `device` plus the banded hint."""
+    tiny = torch.finfo(torch.float32).tiny
+    if initial is None:
+        initial = torch.full(
+            (states,), math.log((1. / states) + tiny), dtype=torch.float32, device=device)
+    else:
+        if not log_probs:
+            initial = torch.log(initial)
+        initial = initial.to(device=device, dtype=torch.float32)
+    if transition is None:
+        transition = torch.full(
+            (states, states), math.log(1. / states), dtype=torch.float32, device=device)
+    else:
+        if not log_probs:
+            transition = torch.log(transition)
+        transition = transition.to(dtype=torch.float32)
+    if banded is None:
+        banded = batch >= 32 and _is_banded(transition)
+    return transition.to(device=device), initial, banded
+
+
+def _from_probabilities_packed(observation, item_row, batch_frames, transition, initial, log_probs, device,
+                               banded=None, min_chunk_size=None, entropy_threshold=None, stats=None):
+    """from_probabilities on a PACKED batch: `observation` (rows, states), item i in rows item_row[i] ..
+    + batch_frames[i] (host or device tensor; fp32 / fp16 / bf16).  With `min_chunk_size` every item is
+    first cut at its low-entropy frames (chunk.py:12-85, entropy on the device over the whole buffer in
+    one pass) and the pieces -- row ranges of the same buffer -- are decoded as independent items, which
+    is what the reference's Dataset + collate + separate do (data/dataset.py:21-23, collate.py:13-17,
+    36-45).  Returns (rows,) int32 on `device`: every item's states in its own rows."""
+    import importlib
+    chunk_module = importlib.import_module(__package__ + '.chunk')   # (the package attribute `chunk` is the function)
+    rows, states = observation.shape
+    frames_list = [int(f) for f in batch_frames]
+    rows_list = [int(r) for r in item_row]
+    model_transition, model_initial, banded = _prepare_model(
+        states, len(frames_list), transition, initial, log_probs, device, banded)
+    flags = _ffi.EPS_FLOOR
+    if not log_probs:
+        if observation.dtype == torch.float32:
+            flags |= _ffi.OBS_IS_PROBABILITY
+        else:
+            # the reference takes the log in the INPUT dtype, then casts (core.py:190-191)
+            observation = torch.log(observation)
+    raw = observation
+    dtype = observation.dtype if observation.dtype in (torch.float16, torch.bfloat16) else torch.float32
+    if min_chunk_size is not None and not log_probs and observation.dtype != torch.float32:
+        raise ValueError('chunked decoding of non-fp32 probability files is not supported on the packed route')
+    observation = observation.to(device=device, dtype=dtype, non_blocking=True)
+    if min_chunk_size is not None:
+        # the reference chunks the observation exactly as stored (before any conversion)
+        del raw
+        low = chunk_module.low_entropy_frames_device(
+            observation, torbi_b200.ENTROPY_THRESHOLD if entropy_threshold is None else entropy_threshold, stats)
+        piece_row, piece_frames = [], []
+        for row0, frames in zip(rows_list, frames_list):
+            points = chunk_module.split_points_from_candidates(low[row0:row0 + frames], frames, min_chunk_size)
+            bounds = [0] + points + [frames]
+            for start, stop in zip(bounds[:-1], bounds[1:]):
+                piece_row.append(row0 + start)
+                piece_frames.append(stop - start)
+        rows_list, frames_list = piece_row, piece_frames
+        if stats is not None:
+            stats['pieces'] = stats.get('pieces', 0) + len(piece_row)
+    if banded:
+        flags |= _ffi.BANDED
+    with timing.context('torbi', device):                    # core.py:200
+        return decode_packed(observation, torch.tensor(rows_list, dtype=torch.int64),
+                             torch.tensor(frames_list, dtype=torch.int32), model_transition, model_initial, flags=flags)
+
+
 def _from_probabilities_one(observation, batch_frames, transition, initial, log_probs,
                             device, mode, return_posterior=False, banded=None):
     batch, frames, states = observation.shape
@@ -176,8 +265,9 @@ def _from_probabilities_one(observation, batch_frames, transition, initial, log_
     observation, flags = _prepare_observation(observation, log_probs, device, mode)
     if banded:
         flags |= _ffi.BANDED
-    return decode(observation, batch_frames, transition, initial, flags=flags,
-                  return_posterior=return_posterior)
+    with timing.context('torbi', device):                    # core.py:200
+        return decode(observation, batch_frames, transition, initial, flags=flags,
+                      return_posterior=return_posterior)
 
 
 def from_probabilities(
@@ -384,11 +474,10 @@ def from_files_to_files(
     # batch small.  The reference batches in the given order (loader.py:19-25).
     sizes = [os.path.getsize(file) for file in input_files]
 
-    # Whole files, in-process loading: the native pipeline (C++ reader / writer threads, pinned
-    # ring of batch buffers).  Chunked decoding (MIN_CHUNK_SIZE) and worker-process loaders keep
-    # the DataLoader route of the reference.
-    native = torbi_b200.MIN_CHUNK_SIZE is None and torbi_b200.NUM_WORKERS == 0 and \
-        os.environ.get('TORBI_B200_NATIVE_IO', '1') != '0'
+    # In-process loading: the native pipeline (C++ reader / writer threads, pinned ring of packed
+    # batch buffers, entropy chunking on the device when MIN_CHUNK_SIZE is set).  Worker-process
+    # loaders keep the DataLoader route of the reference.
+    native = torbi_b200.NUM_WORKERS == 0 and os.environ.get('TORBI_B200_NATIVE_IO', '1') != '0'
 
     def run(files, file_sizes, device, progress, io_threads):
         if native:
@@ -437,17 +526,29 @@ def _from_files_native(input_files, sizes, mapping, transition, initial, log_pro
                        io_threads, batch_bytes=1 << 29, depth=2):
     """The file pipeline of one GPU.  A loader thread fills a ring of `depth + 1` pinned batch
     buffers through the native reader (csrc/ptfile.cpp: central directory + pickle parsed in
-    C++, payloads pread() straight into the padded batch by `io_threads` host threads) while
-    the GPU decodes the previous batch; results are written by the native writer on a third
-    thread.  Per file the work is the reference's (torch.load -> pad -> decode -> torch.save of
-    an int32 (frames,) tensor, core.py:376-463), only the plumbing differs."""
+    C++, payloads pread() straight into the batch by `io_threads` host threads) while the GPU
+    decodes the previous batch; results are written by the native writer on a third thread.
+    Batches are PACKED: the files lie back to back in one (rows, states) buffer, nothing is padded
+    to the longest file (collate.py:26-31 pads), neither on the bus nor in the score history; with
+    MIN_CHUNK_SIZE the files are cut at their low-entropy frames on the device (chunk.py:12-85) and
+    the pieces decoded in place.  Per file the result is the reference's (torch.load -> [chunk] ->
+    pad -> decode -> [join] -> torch.save of an int32 (frames,) tensor, core.py:376-463), only the
+    plumbing differs.  TORBI_B200_PACKED=0 keeps the padded batches of the reference."""
     from .data import native as native_io
 
-    batches = size_bucketed_batches(sizes, torbi_b200.BATCH_SIZE, max_padded_bytes=batch_bytes)
+    packed = os.environ.get('TORBI_B200_PACKED', '1') != '0'
+    chunked = torbi_b200.MIN_CHUNK_SIZE is not None
+    if packed:
+        batches = size_capped_batches(sizes, torbi_b200.BATCH_SIZE, max_bytes=batch_bytes)
+    else:
+        batches = size_bucketed_batches(sizes, torbi_b200.BATCH_SIZE, max_padded_bytes=batch_bytes)
     if not batches:
         return
     # file size bounds the payload, the first file of a batch is its largest
-    numel = max(len(batch) * int(sizes[batch[0]]) for batch in batches) // 4 + 1
+    if packed:
+        numel = max(sum(int(sizes[i]) for i in batch) for batch in batches) // 4 + 1
+    else:
+        numel = max(len(batch) * int(sizes[batch[0]]) for batch in batches) // 4 + 1
     pin = torch.cuda.is_available()
     free: queue.Queue = queue.Queue()
     for _ in range(depth + 1):
@@ -473,14 +574,23 @@ def _from_files_native(input_files, sizes, mapping, transition, initial, log_pro
                 if got is None:
                     return
                 buffer = got[0]
-                loaded = native_io.load_batch(files, threads=io_threads, out=buffer)
+                loaded = None
+                if packed:
+                    loaded = native_io.load_batch_packed(files, threads=io_threads, out=buffer)
+                elif not chunked:
+                    loaded = native_io.load_batch(files, threads=io_threads, out=buffer)
+                    if loaded is not None:
+                        loaded = (loaded[0], None, loaded[1], None)
                 if loaded is None:
-                    # mixed dtypes / widths: the reference's own collate (file dtype kept, cast later)
+                    # mixed dtypes / widths / legacy files: the reference's own Dataset (which chunks on
+                    # the CPU when MIN_CHUNK_SIZE is set) and collate (file dtype kept, cast later)
                     dataset = torbi_b200.data.Dataset(files)
-                    observation, batch_frames, _, _ = torbi_b200.data.collate(
+                    observation, batch_frames, batch_chunks, _ = torbi_b200.data.collate(
                         [dataset[i] for i in range(len(files))], pin_memory=pin)
-                    loaded = (observation, batch_frames)
-                if handoff(ready, (loaded[0], loaded[1], files, buffer)) is None:
+                    loaded = (observation, None, batch_frames, batch_chunks)
+                elif len(loaded) == 3:
+                    loaded = (loaded[0], loaded[1], loaded[2], None)
+                if handoff(ready, (loaded, files, buffer)) is None:
                     return
             handoff(ready, done)
         except BaseException as error:  # noqa: BLE001 - re-raised by the consumer
@@ -504,18 +614,32 @@ def _from_files_native(input_files, sizes, mapping, transition, initial, log_pro
                 break
             if isinstance(item, BaseException):
                 raise item
-            observation, batch_frames, files, buffer = item
-            indices = from_probabilities(
-                observation=observation,
-                batch_frames=batch_frames,
-                transition=transition,
-                initial=initial,
-                log_probs=log_probs,
-                gpu=device,
-                banded=(banded and len(files) >= 32) if banded is not None else None)
-            indices = indices.cpu()            # also orders the host->device copy before the buffer is reused
-            free.put(buffer)
-            rows = [indices[i, :int(frames)] for i, frames in enumerate(batch_frames)]      # core.py:452-457
+            (observation, item_row, batch_frames, batch_chunks), files, buffer = item
+            use_banded = (banded and len(files) >= 32) if banded is not None else None
+            if item_row is not None:
+                indices = _from_probabilities_packed(
+                    observation, item_row, batch_frames, transition, initial, log_probs,
+                    torch.device(f'cuda:{device}'), banded=use_banded,
+                    min_chunk_size=torbi_b200.MIN_CHUNK_SIZE, stats=_PIPELINE_STATS)
+                indices = indices.cpu()        # also orders the host->device copy before the buffer is reused
+                free.put(buffer)
+                rows = [indices[int(row):int(row) + int(frames)] for row, frames in zip(item_row, batch_frames)]
+            else:
+                indices = from_probabilities(
+                    observation=observation,
+                    batch_frames=batch_frames,
+                    transition=transition,
+                    initial=initial,
+                    log_probs=log_probs,
+                    gpu=device,
+                    banded=use_banded)
+                indices = indices.cpu()
+                free.put(buffer)
+                if batch_chunks is not None and chunked:
+                    rows = [r.to(torch.int32) for r in torbi_b200.data.separate(                # core.py:438-448
+                        indices=indices, batch_chunks=batch_chunks, batch_frames=batch_frames)]
+                else:
+                    rows = [indices[i, :int(frames)] for i, frames in enumerate(batch_frames)]  # core.py:452-457
             pending.append(saver.submit(native_io.save_int32, rows, [mapping[file] for file in files],
                                         io_threads))
             if bar is not None:
@@ -530,6 +654,10 @@ def _from_files_native(input_files, sizes, mapping, transition, initial, log_pro
         saver.shutdown(wait=True)
         if bar is not None:
             bar.close()
+
+
+# counters of the last file pipelines (frames seen / re-checked by the device chunker, pieces decoded)
+_PIPELINE_STATS: Dict[str, int] = {}
 
 
 ###############################################################################

@@ -910,6 +910,27 @@ int torbi_b200_decode_host_packed(const void *observation, const int64_t *item_r
     });
 }
 
+int torbi_b200_entropy(const void *observation, int64_t rows, int64_t S, uint32_t flags, float *entropy,
+                       void *stream) {
+    g_error[0] = 0;
+    if (!observation || !entropy) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+    if (rows < 1 || S < 1 || S > 0x7fffffff)
+        return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "rows and states must be >= 1 (got %lld, %lld)", (long long)rows, (long long)S);
+    if ((flags & TORBI_B200_OBS_F16) && (flags & TORBI_B200_OBS_BF16))
+        return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "TORBI_B200_OBS_F16 and TORBI_B200_OBS_BF16 are exclusive");
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
+    DeviceInfo info;
+    int rc = device_info(device, &info);
+    if (rc) return rc;
+    e = launch_entropy(observation, (flags & TORBI_B200_OBS_F16) ? 1 : (flags & TORBI_B200_OBS_BF16) ? 2 : 0, rows, S,
+                       entropy, info.sm_count, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "entropy");
+    g_launches += 1;
+    return TORBI_B200_OK;
+}
+
 int torbi_b200_selftest_conversion(uint64_t *mismatches) {
     g_error[0] = 0;
     if (!mismatches) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "NULL pointer argument");

@@ -74,6 +74,11 @@ cudaError_t launch_gather_checkpoints(const ForwardArgs &a, cudaStream_t stream)
 cudaError_t launch_backtrace_recompute(const Workspace &ws, int32_t *indices, int64_t B, int64_t T,
                                        int64_t S, cudaStream_t stream);
 
+// entropy.cu -- framewise normalised entropy of chunk.py:81-85; out = device (rows, 2) fp32:
+// [H, sum of |terms| / log(states)]
+cudaError_t launch_entropy(const void *observation, int obs_dtype, int64_t rows, int64_t S, float *out,
+                           int sm_count, cudaStream_t stream);
+
 // selftest.cu
 cudaError_t launch_selftest_conversion(unsigned long long *mismatches, int sm_count, cudaStream_t stream);
 

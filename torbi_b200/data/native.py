@@ -77,6 +77,43 @@ def load_batch(files: Sequence, pin_memory: bool = False, threads: int = 0, out:
     return observation, batch_frames
 
 
+def load_batch_packed(files: Sequence, pin_memory: bool = False, threads: int = 0, out: torch.Tensor = None):
+    """The files of a batch back to back in ONE (rows, S) buffer -- no zero padding to the longest
+    file (the reference pads, collate.py:26-31): returns (observation, item_row, batch_frames) with
+    file i in rows item_row[i] .. item_row[i] + batch_frames[i], in the files' own dtype (fp32, fp16
+    or bf16), or None when the batch needs the generic path (see load_batch).  This is the layout
+    torbi_b200.decode_packed / decode_host_packed take."""
+    infos = inspect(files, threads)
+    shapes, dtypes = [], set()
+    for info in infos:
+        if info.status != _ffi.PT_OK:
+            return None
+        shapes.append(tuple(info.shape[:info.ndim]))
+        dtypes.add(DTYPES[info.dtype])
+    if len(dtypes) != 1 or not dtypes <= {torch.float32, torch.float16, torch.bfloat16} or \
+            any(len(shape) != 2 or shape[0] < 1 for shape in shapes) or len({shape[1] for shape in shapes}) != 1:
+        return None
+    dtype = next(iter(dtypes))
+    itemsize = 4 if dtype == torch.float32 else 2
+    states = shapes[0][1]
+    batch_frames = torch.tensor([shape[0] for shape in shapes], dtype=torch.int32)
+    item_row = torch.zeros(len(files), dtype=torch.int64)
+    item_row[1:] = torch.cumsum(batch_frames.to(torch.int64), 0)[:-1]
+    rows = int(batch_frames.sum())
+    if out is not None and out.numel() * out.element_size() >= rows * states * itemsize:
+        observation = out.view(dtype)[:rows * states].view(rows, states)
+    else:
+        observation = torch.empty((rows, states), dtype=dtype, pin_memory=pin_memory)
+    array, _keep = _paths(files)
+    row_bytes = states * itemsize
+    destinations = (ctypes.c_void_p * len(files))(*[observation.data_ptr() + int(r) * row_bytes for r in item_row])
+    capacities = (ctypes.c_int64 * len(files))(*[int(f) * row_bytes for f in batch_frames])
+    failed = _ffi.library().torbi_b200_pt_read(array, infos, len(files), destinations, capacities, threads)
+    if failed:
+        raise OSError(f'torbi_b200: reading {failed} of {len(files)} files failed')
+    return observation, item_row, batch_frames
+
+
 def save_int32(tensors: List[torch.Tensor], files: Sequence, threads: int = 0):
     """torch.save() of contiguous CPU int32 tensors (core.py:466-473), written by native threads."""
     tensors = [tensor.contiguous() for tensor in tensors]

@@ -1,9 +1,6 @@
-"""Evaluation helpers for pitch posteriorgram decoding, the decode-facing part
-of /root/reference/torbi/evaluate/{core,metrics}.py.  The reference harness needs
-`penn`, `librosa` and downloaded datasets; what is kept here is what exercises
-the decoder: the pitch transition matrix recipe and the raw-pitch-accuracy
-metric, usable with synthetic posteriorgrams.
-"""
+"""Metrics of /root/reference/torbi/evaluate/metrics.py (raw pitch accuracy at several thresholds) and
+the pitch transition matrix recipe of evaluate/core.py:23-34, with penn's constants written out (penn is
+not importable offline)."""
 from typing import Dict, Iterable, Sequence
 
 import torch
