@@ -97,6 +97,11 @@ extern "C" {
  * between the batches of its group, so one batch's score exchange through L2 is hidden behind the
  * other's max-plus loop.  Score-history mode, dense transitions, states <= 20 x (#SM / 2). */
 #define TORBI_B200_FORCE_CLUSTER (1u << 19)
+/* force the flow kernel: one sequence at a time on all SMs, every timestep exchanged as 8-byte
+ * {score, step tag} words through L2 (single 64-bit stores polled by their consumers: no grid barrier,
+ * no atomics), the transition block resident in registers + shared memory.  The decomposition for one
+ * or a few sequences (config 1, config 5); states <= 64 x #SM.  Stores uint16 backpointers. */
+#define TORBI_B200_FORCE_FLOW (1u << 20)
 /* (bit 14 was the warp-specialised variant of the tiled kernel: measured slower, no longer built;
  * source and experiment log kept under tools/experiments/ and profiles/r01_ws_experiment.txt) */
 

@@ -92,7 +92,7 @@ def test_strong_scaling_share_of_config2(oracle):
 @pytest.mark.parametrize('kernel,flags', [
     ('auto', 0), ('generic', _ffi.FORCE_GENERIC), ('wide', _ffi.FORCE_WIDE), ('tiled64', _ffi.TILE_ROWS_64),
     ('tiled16bp', _ffi.TILE_ROWS_16 | _ffi.BACKPOINTERS), ('banded', _ffi.BANDED), ('split', _ffi.FORCE_SPLIT),
-    ('split_streamed', _ffi.FORCE_SPLIT | _ffi.SPLIT_STREAMED), ('cluster', _ffi.FORCE_CLUSTER)])
+    ('split_streamed', _ffi.FORCE_SPLIT | _ffi.SPLIT_STREAMED), ('cluster', _ffi.FORCE_CLUSTER), ('flow', _ffi.FORCE_FLOW)])
 @pytest.mark.parametrize('states', [1440, 333])
 def test_half_precision_observations_are_upcast_exactly(states, kernel, flags, dtype, oracle):
     """The reference casts the observation to fp32 on the host (core.py:191); here the 2-byte
@@ -137,7 +137,7 @@ def test_half_precision_through_the_python_api_and_the_host_entry(dtype, oracle)
 
 @pytest.mark.parametrize('kernel,flags', [('wide', _ffi.FORCE_WIDE), ('generic', _ffi.FORCE_GENERIC),
                                           ('tiled', _ffi.FORCE_TILED), ('split', _ffi.FORCE_SPLIT),
-                                          ('cluster', _ffi.FORCE_CLUSTER)])
+                                          ('cluster', _ffi.FORCE_CLUSTER), ('flow', _ffi.FORCE_FLOW)])
 def test_checkpoints_hold_the_forward_scores(kernel, flags, oracle):
     obs, frames, A, init = random_problem(91, 5, 40, 257, quant=2)
     every = 7
@@ -167,7 +167,7 @@ def test_blocked_backtrace_equals_the_plain_chase(shape, oracle):
     B, T, S = shape
     obs, frames, A, init = random_problem(T + S, B, T, S, quant=2, transition='dense')
     want = oracle.c_decode(obs, frames, A, init, exact_scan=False)
-    for flags in (_ffi.FORCE_WIDE, _ffi.FORCE_GENERIC):
+    for flags in (_ffi.FORCE_WIDE, _ffi.FORCE_GENERIC, _ffi.FORCE_FLOW):
         indices, _ = gpu_decode(obs, frames, A, init, flags=flags)
         assert _ffi.library().torbi_b200_last_backtrace().decode() == 'backtrace_blocked'
         assert np.array_equal(indices, want)
@@ -193,7 +193,7 @@ def test_config5_long_sequence_verified_in_segments(oracle):
     frames = torch.tensor([T], dtype=torch.int32)
     indices, posterior, checkpoints = torbi_b200.decode(obs, frames, A, init, return_posterior=True,
                                                         checkpoint_every=every)
-    assert last_kernel() == 'forward_wide'
+    assert last_kernel() in ('forward_wide', 'forward_flow')
     assert _ffi.library().torbi_b200_last_backtrace().decode() == 'backtrace_blocked'
     path = indices[0].cpu().numpy()
     A_host = A.cpu().numpy()
@@ -281,7 +281,7 @@ def test_banded_hint_on_a_state_space_too_wide_for_the_tiled_kernel(oracle):
     B, T, S = 32, 3, 12000
     obs = torch.from_numpy(cases.log_softmax(rng.standard_normal((B, T, S))))
     got = torbi_b200.from_probabilities(obs, None, None, None, log_probs=True, gpu=0)
-    assert last_kernel() in ('forward_wide', 'forward_generic')
+    assert last_kernel() in ('forward_wide', 'forward_generic', 'forward_flow')
     want = oracle.ref_from_probabilities(obs, None, None, None, True)
     assert np.array_equal(got.cpu().numpy(), want)
     lib = _ffi.library()
@@ -328,7 +328,8 @@ def test_failed_host_call_leaves_the_arena_usable(oracle):
 @pytest.mark.parametrize('kernel,flags', [
     ('tiled16', _ffi.TILE_ROWS_16), ('tiled32', _ffi.TILE_ROWS_32), ('tiled16bp', _ffi.TILE_ROWS_16 | _ffi.BACKPOINTERS),
     ('banded16', _ffi.TILE_ROWS_16 | _ffi.BANDED), ('split', _ffi.FORCE_SPLIT),
-    ('split_streamed', _ffi.FORCE_SPLIT | _ffi.SPLIT_STREAMED), ('cluster', _ffi.FORCE_CLUSTER), ('wide', _ffi.FORCE_WIDE)])
+    ('split_streamed', _ffi.FORCE_SPLIT | _ffi.SPLIT_STREAMED), ('cluster', _ffi.FORCE_CLUSTER), ('wide', _ffi.FORCE_WIDE),
+    ('flow', _ffi.FORCE_FLOW)])
 def test_ring_stress_many_steps_small_tiles(kernel, flags, oracle, ring_stress_problem):
     """6000 timesteps x small tiles x quantised inputs (exact ties everywhere): tens of thousands of
     ring stages with the warps free to drift apart; any lost or early copy changes a score or a tie."""
@@ -373,7 +374,8 @@ def _packed_problem(seed, lengths, S, gap_rows=(0, 3, 0, 1), transition='dense',
 @pytest.mark.parametrize('kernel,flags', [
     ('auto', 0), ('generic', _ffi.FORCE_GENERIC), ('wide', _ffi.FORCE_WIDE), ('tiled64', _ffi.TILE_ROWS_64),
     ('tiled16bp', _ffi.TILE_ROWS_16 | _ffi.BACKPOINTERS), ('banded', _ffi.BANDED | _ffi.TILE_ROWS_32),
-    ('split', _ffi.FORCE_SPLIT), ('split_streamed', _ffi.FORCE_SPLIT | _ffi.SPLIT_STREAMED), ('cluster', _ffi.FORCE_CLUSTER)])
+    ('split', _ffi.FORCE_SPLIT), ('split_streamed', _ffi.FORCE_SPLIT | _ffi.SPLIT_STREAMED), ('cluster', _ffi.FORCE_CLUSTER),
+    ('flow', _ffi.FORCE_FLOW)])
 @pytest.mark.parametrize('states', [1440, 333])
 def test_packed_layout_matches_oracle(states, kernel, flags, oracle):
     """torbi_b200_decode_packed: ragged items anywhere in one (rows, S) buffer, every kernel; the
@@ -424,3 +426,48 @@ def test_packed_host_entry_and_validation(oracle):
     bad[int(np.argmax(item_row))] = rows - 1                     # runs off the end
     with pytest.raises(ValueError, match='leave the buffer'):
         torbi_b200.decode_packed(cuda(packed), t(bad), t(frames), cuda(A), cuda(init))
+
+
+# ---------------------------------------------------------------------------
+# flow kernel (tagged 8-byte score exchange through L2, no grid barrier)
+# ---------------------------------------------------------------------------
+
+@pytest.mark.parametrize('shape', [
+    # (B, T, S, quant, transition): every register / shared-memory / streamed residency split of the
+    # transition rows, S % 4 != 0, fewer states than CTAs, several sequences back to back (buffer sets
+    # alternate, tags keep counting), one-frame items between long ones
+    (1, 300, 1440, 1, 'triangular'), (1, 120, 1441, 2, 'dense'), (3, 90, 4096, 2, 'dense'), (1, 60, 4099, None, 'dense'),
+    (5, 70, 333, 2, 'dense'), (4, 50, 7, 1, 'dense'), (2, 40, 96, None, 'dense'), (2, 25, 6000, 2, 'dense'),
+    (1, 12, 9400, 1, 'dense'), (6, 200, 2500, 2, 'dense'), (1, 2000, 640, 2, 'dense'),
+], ids=lambda s: f'B{s[0]}-T{s[1]}-S{s[2]}')
+def test_flow_kernel_matches_oracle(shape, oracle):
+    B, T, S, quant, transition = shape
+    obs, frames, A, init = random_problem(B * 31 + S, B, T, S, quant=quant, transition=transition)
+    if B >= 3:
+        frames[1] = 1                                            # no recursion step at all
+        frames[2] = T
+    want_idx, want_post = oracle.c_decode(obs, frames, A, init, exact_scan=False, want_posterior=True)
+    indices, posterior = gpu_decode(obs, frames, A, init, flags=_ffi.FORCE_FLOW)
+    assert last_kernel() == 'forward_flow'
+    assert np.array_equal(indices, want_idx)
+    assert np.array_equal(bits(posterior), bits(want_post))
+    # twice more on the same workspace pattern: stale tags of an earlier call must never match
+    for _ in range(2):
+        again, _ = gpu_decode(obs, frames, A, init, flags=_ffi.FORCE_FLOW)
+        assert np.array_equal(again, want_idx)
+
+
+def test_flow_kernel_is_what_single_sequences_get(oracle):
+    """BASELINE config 1 shape (S=1440, B=1, T=2000, uniform transition / initial) through the selector."""
+    rng = np.random.default_rng(1)
+    obs = torch.from_numpy(cases.log_softmax(rng.standard_normal((1, 2000, 1440))))
+    got = torbi_b200.from_probabilities(obs, None, None, None, log_probs=True, gpu=0)
+    assert last_kernel() == 'forward_flow'
+    want = oracle.ref_from_probabilities(obs, None, None, None, True)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_flow_kernel_rejects_very_wide_state_spaces():
+    obs, frames, A, init = random_problem(1, 1, 2, 12000, ragged=False)
+    with pytest.raises(ValueError, match='flow kernel does not support'):
+        gpu_decode(obs, frames, A, init, flags=_ffi.FORCE_FLOW)

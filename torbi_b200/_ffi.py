@@ -35,6 +35,7 @@ BACKPOINTERS = 1 << 16
 FORCE_SPLIT = 1 << 17
 SPLIT_STREAMED = 1 << 18
 FORCE_CLUSTER = 1 << 19
+FORCE_FLOW = 1 << 20
 
 ABI_VERSION = 3
 

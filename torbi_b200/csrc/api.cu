@@ -156,9 +156,10 @@ size_t torbi_b200_workspace_bytes(int64_t B, int64_t T, int64_t S, uint32_t flag
 
 namespace {
 
-enum Choice { kGeneric, kTiled, kWide, kSplit, kCluster };
+enum Choice { kGeneric, kTiled, kWide, kSplit, kCluster, kFlow };
 // whether the cost model may pick the cluster kernel by itself (else only TORBI_B200_FORCE_CLUSTER does)
 constexpr bool kClusterAuto = false;
+constexpr int64_t kFlowAutoMaxBatch = 16;
 
 // Kernel selection: estimated time of the batch-tiled, split-K, cluster and wide decompositions for
 // this length profile (`sorted` = batch_frames, longest first), unless a flag forces one.  Also fixes
@@ -192,7 +193,14 @@ int choose_kernel(ForwardArgs &a, const std::vector<int32_t> &sorted, uint32_t &
         const double seconds = cluster_estimate_seconds(sorted.data(), B, S, a.sm_count);
         if (seconds < best_seconds) { choice = kCluster; best_seconds = seconds; }
     }
-    if (can_wide && wide_estimate_seconds(sorted.data(), B, S, a.sm_count) < best_seconds) choice = kWide;
+    if (can_wide) {
+        const double seconds = wide_estimate_seconds(sorted.data(), B, S, a.sm_count);
+        if (seconds < best_seconds) { choice = kWide; best_seconds = seconds; }
+    }
+    const bool can_flow = forward_flow_supported(a);
+    // (sequences go through the flow kernel one after the other: chosen by itself only for a handful)
+    if (can_flow && B <= kFlowAutoMaxBatch && flow_estimate_seconds(sorted.data(), B, S, a.sm_count) < best_seconds)
+        choice = kFlow;
     if (flags & TORBI_B200_FORCE_SPLIT) {
         if (!can_split)
             return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "split kernel does not support this shape / these flags");
@@ -211,6 +219,10 @@ int choose_kernel(ForwardArgs &a, const std::vector<int32_t> &sorted, uint32_t &
         if (!can_wide) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "wide kernel does not support this shape");
         choice = kWide;
     }
+    if (flags & TORBI_B200_FORCE_FLOW) {
+        if (!can_flow) return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "flow kernel does not support this shape");
+        choice = kFlow;
+    }
     if (flags & TORBI_B200_FORCE_GENERIC) choice = kGeneric;
     *out = choice;
     return TORBI_B200_OK;
@@ -224,6 +236,7 @@ const char *kernel_name(int tile_rows, Choice choice, uint32_t flags) {
     }
     if (choice == kSplit) return "forward_split";
     if (choice == kCluster) return "forward_cluster";
+    if (choice == kFlow) return "forward_flow";
     return choice == kWide ? "forward_wide" : "forward_generic";
 }
 
@@ -402,13 +415,15 @@ int decode_device(const void *observation, const int32_t *batch_frames,
     }
 
     const Choice choice = plan.choice;
-    const bool tiled = choice != kGeneric;               // kernels that honour frames_ready
+    const bool tiled = choice != kGeneric && choice != kFlow;   // kernels that honour frames_ready
     if (opt.streamed) *opt.streamed = tiled;
     g_last_kernel = kernel_name(plan.tile_rows, choice, flags);
+    if (!tiled && opt.frames_ready)
+        return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "internal: this kernel cannot stream");
     if (choice == kGeneric) {
-        if (opt.frames_ready)
-            return fail(TORBI_B200_ERR_INVALID_ARGUMENT, "internal: generic kernel cannot stream");
         e = launch_forward_generic(a, stream);
+    } else if (choice == kFlow) {
+        e = launch_forward_flow(a, stream);
     } else if (choice == kWide) {
         e = launch_forward_wide(a, stream);
     } else if (choice == kSplit) {
@@ -422,7 +437,7 @@ int decode_device(const void *observation, const int32_t *batch_frames,
         e = launch_forward_tiled(a, stream);
     }
     if (e != cudaSuccess) return fail_cuda(e, g_last_kernel);
-    int launches = tiled ? (choice == kTiled && (flags & TORBI_B200_BANDED) ? 3 : 2) : 1;   // (pad_transition + [analyze_band] +) forward
+    int launches = choice == kGeneric ? 1 : (choice == kTiled && (flags & TORBI_B200_BANDED) ? 3 : 2);   // (pad_transition + [analyze_band] +) forward
     if (opt.checkpoints && plan.history) {
         // the score history holds every P_t already: gather the requested rows
         e = launch_gather_checkpoints(a, stream);
@@ -661,7 +676,7 @@ int decode_items_on_device(const void *observation_, const int32_t *batch_frames
     const bool pinned = cudaPointerGetAttributes(&attr, observation) == cudaSuccess &&
                         attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    const bool stream_in = pinned && plan.choice != kGeneric && T >= 64 && row_bytes < (size_t(1) << 31) &&
+    const bool stream_in = pinned && plan.choice != kGeneric && plan.choice != kFlow && T >= 64 && row_bytes < (size_t(1) << 31) &&
                            (size_t)count * row_bytes >= (size_t(64) << 20);
     const int chunks = stream_in ? (int)std::min<int64_t>(kMaxChunks, std::max<int64_t>(2, T / 16)) : 1;
     // Chunk boundaries along T.  The forward kernel trails the copy by one chunk (step t needs the whole

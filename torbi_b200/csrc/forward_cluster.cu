@@ -293,11 +293,17 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
         lc = cc;
         int lstage = 0;                                         // stage of `lc`'s batch-step to issue next
         unsigned issued = 0, consumed = 0;                      // ring stages; slot = count % kSlots
-        // issue the next ring stage of this warp (an empty group once the schedule is exhausted)
-        auto issue_next = [&]() {
+        // Issue the next ring stage of this warp (nothing once the schedule is exhausted).  The first
+        // stage of a batch-step needs the batch's previous step published by EVERY CTA of the group --
+        // this one included.  While a group still interleaves several batches that is some other
+        // batch's step; once a single batch is left it is the very step this warp is computing, so the
+        // look-ahead issue (`may_block` false, from inside the K loop) is skipped and the stage is
+        // issued at the top of the next batch-step instead, after this CTA's own publish.
+        auto issue_next = [&](bool may_block) {
             if (lc.n > 0 && ns > 0) {
                 const int64_t row0 = (int64_t)global_batch(lc.b) * TM;
                 if (lstage == 0 && lc.tau > 1) {
+                    if (!may_block && lc.b == cc.b) return;
                     // P_{tau-1} of this batch must have been published by every CTA of the group
                     const unsigned *counter = p.sync + (size_t)kSyncStride * (1 + global_batch(lc.b));
                     const unsigned target = group_ctas * (unsigned)(lc.tau - 1);
@@ -317,11 +323,10 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
                     lstage = 0;
                     cursor_next(lc, s_len);
                 }
+                cp_async_commit();
+                ++issued;
             }
-            cp_async_commit();
-            ++issued;
         };
-        issue_next();
 
         CPROF_DECL
         while (cc.n > 0) {
@@ -352,9 +357,10 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
                 for (int c = 0; c < N; ++c) cur[i][c] = -INFINITY;
 
             for (int st = 0; st < ns; ++st) {
+                if (issued == consumed) issue_next(true);       // nothing in flight: this very stage (see issue_next)
                 cp_async_wait_all();                            // this lane's copies of the stage have landed ...
                 __syncwarp();                                   // ... and so have the other lanes'; all lanes are past the previous stage
-                issue_next();                                   // into the slot read one stage ago
+                issue_next(false);                              // into the slot read one stage ago
                 const float *Ps = wring + (consumed % kSlots) * kSlotFloats + lane_b * kRowStride;
                 const float *As = Aw + st * (kStageSteps * 4);
                 ++consumed;

@@ -56,6 +56,12 @@ bool forward_wide_supported(const ForwardArgs &a);
 double wide_estimate_seconds(const int32_t *frames_sorted, int64_t B, int64_t S, int sm_count);
 cudaError_t launch_forward_wide(const ForwardArgs &a, cudaStream_t stream);
 
+// forward_flow.cu -- one sequence at a time on all SMs, timesteps exchanged as tagged 8-byte words
+// through L2 (no grid barrier), transition block resident in registers + shared memory
+bool forward_flow_supported(const ForwardArgs &a);
+double flow_estimate_seconds(const int32_t *frames_sorted, int64_t B, int64_t S, int sm_count);
+cudaError_t launch_forward_flow(const ForwardArgs &a, cudaStream_t stream);
+
 // backtrace.cu -- ragged backtrace + tail fill (viterbi.cpp:140-160, :219-221)
 cudaError_t launch_backtrace(const Workspace &ws, int32_t *indices, int64_t B, int64_t T,
                              int64_t S, cudaStream_t stream);
