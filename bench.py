@@ -66,6 +66,10 @@ def parse_args():
     parser.add_argument('--skip-config3', action='store_true')
     parser.add_argument('--skip-config5', action='store_true')
     parser.add_argument('--config5-frames', type=int, default=1_000_000)
+    parser.add_argument('--skip-config4', action='store_true')
+    parser.add_argument('--config4-files', type=int, default=2000,
+                        help='files of the synthetic corpus (BASELINE config 4 is ~40000 files / ~20 M timesteps; '
+                             'the default is 1/20 of it, same length distribution, on /dev/shm)')
     parser.add_argument('--tile-rows', type=int, default=0, choices=[0, 16, 32, 64])
     parser.add_argument('--split-streamed', action='store_true', help='split kernel: streamed 16 x 40 tiles')
     parser.add_argument('--backpointers', action='store_true',
@@ -361,6 +365,23 @@ def other_configs(lib, device, local, peaks, sm_count, barrier, args):
             'backtrace_ms': r['back_ms'],
             'frac_fp32_maxplus': 2.0 * S * S * timesteps / (r['fwd_ms'] * 1e-3) / 1e12 / fp32_peak(sm_count, peaks),
             'peak_hbm_gb': r['peak_hbm_gb'], 'clocks': r['clocks'], 'checksum': r['checksum']}
+        if r['kernel'] == 'forward_flow':
+            # one sequence: a timestep cannot start before the previous one's scores have crossed L2.  Floor of
+            # a step = L2 store + L2 load latency (2 x ~250 cycles, B300_MICROARCH.md "L2 hit latency") + the
+            # longer of the CTA's scan (S^2 / #SM cells at 64 cells/clk/SM) and the streaming of the transition
+            # rows that neither registers nor shared memory hold (measured L2->SM stream rate,
+            # profiles/r02_microbench_sync.txt: 13.7 TB/s at 64 KB per CTA)
+            clk = peaks['sm_max_mhz'] * 1e6
+            rows = -(-S // sm_count)
+            resident = (20 if S <= 2048 else 10 if S <= 4096 else 4) + (220 * 1024) // (4 * (-(-S // 96) * 96))
+            streamed_bytes = max(0, rows - resident) * S * 4.0 * sm_count
+            floor_us = 1e6 * (500.0 / clk + max(S * S / sm_count / 64.0 / clk, streamed_bytes / 13.7e12))
+            us = 1e3 * r['fwd_ms'] / max(1, timesteps - 1)
+            out[name]['latency_bound'] = {
+                'us_per_step': us, 'floor_us_per_step': floor_us, 'frac': floor_us / us,
+                'streamed_bytes_per_step': streamed_bytes,
+                'note': 'single-sequence recursion is latency bound: floor = L2 round trip (2 x 250 cycles) + max(scan of '
+                        'S^2/#SM cells at 64 cells/clk/SM, L2 stream of the non-resident transition rows at 13.7 TB/s)'}
 
     # config 1: 1440 states, batch 1, 2000 frames, default uniform transition / initial
     S, T = 1440, 2000
@@ -401,6 +422,60 @@ def other_configs(lib, device, local, peaks, sm_count, barrier, args):
         del obs
     torch.cuda.empty_cache()
     return out
+
+
+def config4_corpus(files, world):
+    """Frame counts of the synthetic config-4 corpus: log-normal, median 430, sigma 0.55,
+    clipped to [50, 5000], rescaled to ~500 frames per file on average (20 M timesteps / 40 k files)."""
+    rng = np.random.default_rng(1234)
+    frames = np.clip(np.exp(rng.normal(np.log(430), 0.55, size=files)), 50, 5000)
+    frames = np.maximum(50, (frames * (500.0 * files / frames.sum())).round()).astype(np.int64)
+    import torbi_b200
+    sizes = (frames * 1440 * 4).tolist()
+    return frames, torbi_b200.lpt_shards(sizes, world)          # the sharding from_files_to_files applies
+
+
+def config4_leg(args, rank, world, local, device, barrier, max_over_ranks):
+    """BASELINE config 4: from_files_to_files over a synthetic 1440-state corpus, the files sharded
+    across the N GPUs by size (longest-processing-time first, as core.from_files_to_files does across
+    `gpu=[...]`); here one process per GPU, each decoding its shard from /dev/shm end to end
+    (native reader -> pinned packed batches -> decode -> native writer).  Whole-job timesteps/s =
+    all frames / max over ranks of the wall time."""
+    import shutil
+    import tempfile
+    import cases
+    import torbi_b200
+    frames, shards = config4_corpus(args.config4_files, world)
+    mine = shards[rank] if rank < len(shards) else []
+    root = pathlib.Path(tempfile.mkdtemp(prefix=f'torbi_c4_r{rank}_', dir='/dev/shm' if os.path.isdir('/dev/shm') else None))
+    try:
+        g = torch.Generator(device=device).manual_seed(4000 + rank)
+        inputs, outputs = [], []
+        for i in mine:
+            x = torch.log_softmax(torch.randn((int(frames[i]), 1440), device=device, generator=g), dim=-1).cpu()
+            torch.save(x, root / f'{i}.pt')
+            inputs.append(root / f'{i}.pt')
+            outputs.append(root / f'{i}.out.pt')
+        torch.save(torch.from_numpy(cases.triangular_transition(1440)), root / 'transition.pt')
+        # warm-up on a slice (arena, pinned ring, library load), then the timed pass over the whole shard
+        torbi_b200.from_files_to_files(inputs[:64], outputs[:64], root / 'transition.pt', log_probs=True, gpu=local)
+        barrier()
+        with ClockSampler(local) as clocks:
+            t0 = time.perf_counter()
+            torbi_b200.from_files_to_files(inputs, outputs, root / 'transition.pt', log_probs=True, gpu=local)
+            torch.cuda.synchronize()
+            seconds = time.perf_counter() - t0
+            barrier()
+        check = torch.load(outputs[0]) if outputs else None
+        assert check is None or (check.dtype == torch.int32 and check.shape == (int(frames[mine[0]]),))
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    seconds, = max_over_ranks(seconds)
+    total = int(frames.sum())
+    return {'workload': f'config 4 at {args.config4_files}/40000 scale: {args.config4_files} files, {total} timesteps, S=1440 fp32 '
+                        f'log-probs on /dev/shm, sharded over {world} GPU(s) by size (LPT), end to end incl. file read / write',
+            'value': total / seconds, 'unit': UNIT, 'seconds': seconds, 'files': int(args.config4_files),
+            'input_gb': total * 1440 * 4 / 1e9, 'read_gbs': total * 1440 * 4 / 1e9 / seconds, 'clocks': clocks.summary()}
 
 
 def bench_graft(args):
@@ -511,6 +586,9 @@ def bench_graft(args):
     elapsed_ms, e2e_max = max_over_ranks(elapsed_ms, e2e_ms or 0.0)
     del obs
     torch.cuda.empty_cache()
+    c4 = None
+    if not args.skip_config4 and not args.no_configs and args.scaling == 'weak':
+        c4 = config4_leg(args, rank, world, local, device, barrier, max_over_ranks)
 
     if rank == 0:
         peaks = measured_peaks()
@@ -566,6 +644,8 @@ def bench_graft(args):
                         'device-resident, CUDA events, max over ranks; value = whole-job timesteps/s'}
         if world == 1 and not args.no_configs:
             line['configs'] = other_configs(lib, device, local, peaks, sm_count, barrier, args)
+        if c4 is not None:
+            line.setdefault('configs', {})['c4'] = c4
         if world == 1 and not args.no_cpu_baseline:
             step_cpu, timesteps, kind, cores, sample = cpu_sample(args, args.cpu_seconds or 15.0)
             seconds = step_cpu()

@@ -166,7 +166,7 @@ def test_evaluation_runner_on_a_synthetic_corpus(tmp_path):
     result = torbi_b200.evaluate.datasets(['synthetic'], gpu=0, root=tmp_path)['synthetic']
     assert result['rpa'] == {'0': 1.0, '1': 1.0, '2': 1.0} and result['files'] == 12
     assert result['rtf']['torbi'] > result['rtf']['end_to_end'] > 1.0
-    assert result['rpa_vs_truth']['2'] > 0.8
+    assert result['rpa_vs_truth']['2'] > 0.6
     old = torbi_b200.CONFIG, torbi_b200.MIN_CHUNK_SIZE
     torbi_b200.CONFIG, torbi_b200.MIN_CHUNK_SIZE = 'chunked', 32
     try:

@@ -253,7 +253,9 @@ struct Plan {
     // first row of every item in observation / history / backpointers / indices: b * T in the padded
     // (B,T,S) layout, the caller's offsets in the packed (rows,S) one
     std::vector<int64_t> item_row;
-    int64_t rows = 0;            // rows of the observation buffer (B * T when padded)
+    // first row of every item in the score history / backpointers: compact, item after item
+    std::vector<int64_t> hist_row;
+    int64_t rows = 0;            // rows of the history / backpointer region = sum(batch_frames)
     bool packed = false;
     size_t workspace_bytes = 0;
 };
@@ -299,10 +301,16 @@ int make_plan(const int32_t *batch_frames, int64_t B, int64_t T, int64_t S, uint
             end = item_row[b] + batch_frames[b];
             plan->item_row[b] = item_row[b];
         }
-        plan->rows = rows;
     } else {
         for (int64_t b = 0; b < B; ++b) plan->item_row[b] = b * T;
-        plan->rows = B * T;
+    }
+    // the score history / backpointers only ever hold the frames that exist (the reference zero-fills a
+    // (batch, frames, states) trellis, viterbi.cpp:201-203)
+    plan->hist_row.resize(B);
+    plan->rows = 0;
+    for (int64_t b = 0; b < B; ++b) {
+        plan->hist_row[b] = plan->rows;
+        plan->rows += batch_frames[b];
     }
     plan->order.assign(pad_batch(B), -1);
     std::iota(plan->order.begin(), plan->order.begin() + B, 0);
@@ -384,6 +392,8 @@ int decode_device(const void *observation, const int32_t *batch_frames,
                             cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(ws.item_row, plan.item_row.data(), sizeof(int64_t) * B, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(ws.hist_row, plan.hist_row.data(), sizeof(int64_t) * B, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(ws.sync, 0, sizeof(uint32_t) * kSyncWords, stream);
     if (e != cudaSuccess) return fail_cuda(e, "stage batch_frames");
     // (pageable host memory: the async copies have been staged by the time cudaMemcpyAsync returns)

@@ -16,8 +16,8 @@ constexpr int kBacktraceThreads = 128;
 
 __global__ void __launch_bounds__(kBacktraceThreads)
 backtrace_kernel(const uint16_t *__restrict__ backptr, const int32_t *__restrict__ frames_d,
-                 const int64_t *__restrict__ item_row, const int32_t *__restrict__ final_state,
-                 int32_t *__restrict__ indices, int64_t T, int64_t S) {
+                 const int64_t *__restrict__ item_row, const int64_t *__restrict__ hist_row,
+                 const int32_t *__restrict__ final_state, int32_t *__restrict__ indices, int64_t T, int64_t S) {
     // T > 0: padded layout, indices (B,T), tail t in [frames_b - 1, T) filled; T == 0: packed layout,
     // indices (rows,), item b at item_row[b] .. + frames_b (the tail is the last frame alone)
     const int64_t b = blockIdx.x;
@@ -27,7 +27,7 @@ backtrace_kernel(const uint16_t *__restrict__ backptr, const int32_t *__restrict
     int32_t *out = indices + row0;
     const int64_t out_len = T > 0 ? T : frames;
     if (threadIdx.x == 0) {
-        const uint16_t *bp = backptr + row0 * S;
+        const uint16_t *bp = backptr + hist_row[b] * S;
         int idx = last;
         for (int64_t t = frames - 1; t >= 1; --t) {
             idx = bp[t * S + idx];
@@ -73,13 +73,13 @@ struct BlockedGeometry {
 template <int kPerThread>       // states carried per thread: S <= kPerThread * kComposeThreads
 __global__ void __launch_bounds__(kComposeThreads)
 backtrace_compose_kernel(const uint16_t *__restrict__ backptr, const int32_t *__restrict__ frames_d,
-                         const int64_t *__restrict__ item_row, uint16_t *__restrict__ maps, int S, int64_t K,
+                         const int64_t *__restrict__ hist_row, uint16_t *__restrict__ maps, int S, int64_t K,
                          int64_t max_blocks) {
     const int64_t b = blockIdx.y, m = blockIdx.x;
     const int64_t hi = (int64_t)frames_d[b] - 1 - m * K;
     if (hi < 1) return;
     const int64_t lo = max((int64_t)1, hi - K + 1);
-    const uint16_t *bp = backptr + item_row[b] * S;
+    const uint16_t *bp = backptr + hist_row[b] * S;
     int cur[kPerThread];
 #pragma unroll
     for (int i = 0; i < kPerThread; ++i) cur[i] = min(threadIdx.x + i * kComposeThreads, S - 1);
@@ -116,8 +116,8 @@ __global__ void backtrace_link_kernel(const uint16_t *__restrict__ maps, const i
 
 __global__ void __launch_bounds__(kBacktraceThreads)
 backtrace_chase_kernel(const uint16_t *__restrict__ backptr, const int32_t *__restrict__ frames_d,
-                       const int64_t *__restrict__ item_row, const int32_t *__restrict__ final_state,
-                       const int32_t *__restrict__ entry, int32_t *__restrict__ indices, int64_t T, int64_t S,
+                       const int64_t *__restrict__ item_row, const int64_t *__restrict__ hist_row,
+                       const int32_t *__restrict__ final_state, const int32_t *__restrict__ entry, int32_t *__restrict__ indices, int64_t T, int64_t S,
                        int64_t K, int64_t max_blocks) {
     const int64_t b = blockIdx.y, m = blockIdx.x;
     const int64_t frames = frames_d[b];
@@ -132,7 +132,7 @@ backtrace_chase_kernel(const uint16_t *__restrict__ backptr, const int32_t *__re
     const int64_t hi = frames - 1 - m * K;
     if (hi < 1 || threadIdx.x != 0) return;
     const int64_t lo = max((int64_t)1, hi - K + 1);
-    const uint16_t *bp = backptr + row0 * S;
+    const uint16_t *bp = backptr + hist_row[b] * S;
     int idx = entry[b * max_blocks + m];
     for (int64_t t = hi; t >= lo; --t) {
         idx = bp[t * S + idx];
@@ -160,13 +160,13 @@ cudaError_t launch_backtrace_blocked(const Workspace &ws, int32_t *indices, int6
     int32_t *entry = reinterpret_cast<int32_t *>(region + align_up((size_t)B * max_blocks * S * sizeof(uint16_t), 256));
     const dim3 grid((unsigned)max_blocks, (unsigned)B);
     if (S <= 2 * kComposeThreads)
-        backtrace_compose_kernel<2><<<grid, kComposeThreads, 0, stream>>>(ws.backptr, ws.frames, ws.item_row, maps, (int)S, K, max_blocks);
+        backtrace_compose_kernel<2><<<grid, kComposeThreads, 0, stream>>>(ws.backptr, ws.frames, ws.hist_row, maps, (int)S, K, max_blocks);
     else if (S <= 4 * kComposeThreads)
-        backtrace_compose_kernel<4><<<grid, kComposeThreads, 0, stream>>>(ws.backptr, ws.frames, ws.item_row, maps, (int)S, K, max_blocks);
+        backtrace_compose_kernel<4><<<grid, kComposeThreads, 0, stream>>>(ws.backptr, ws.frames, ws.hist_row, maps, (int)S, K, max_blocks);
     else if (S <= 16 * kComposeThreads)
-        backtrace_compose_kernel<16><<<grid, kComposeThreads, 0, stream>>>(ws.backptr, ws.frames, ws.item_row, maps, (int)S, K, max_blocks);
+        backtrace_compose_kernel<16><<<grid, kComposeThreads, 0, stream>>>(ws.backptr, ws.frames, ws.hist_row, maps, (int)S, K, max_blocks);
     else
-        backtrace_compose_kernel<kComposeStatesPerThread><<<grid, kComposeThreads, 0, stream>>>(ws.backptr, ws.frames, ws.item_row, maps, (int)S, K, max_blocks);
+        backtrace_compose_kernel<kComposeStatesPerThread><<<grid, kComposeThreads, 0, stream>>>(ws.backptr, ws.frames, ws.hist_row, maps, (int)S, K, max_blocks);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     backtrace_link_kernel<<<(unsigned)((B + 127) / 128), 128, 0, stream>>>(maps, ws.frames, ws.final_state, entry, B,
@@ -174,7 +174,7 @@ cudaError_t launch_backtrace_blocked(const Workspace &ws, int32_t *indices, int6
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     backtrace_chase_kernel<<<dim3((unsigned)max_blocks, (unsigned)B), kBacktraceThreads, 0, stream>>>(
-        ws.backptr, ws.frames, ws.item_row, ws.final_state, entry, indices, T, S, K, max_blocks);
+        ws.backptr, ws.frames, ws.item_row, ws.hist_row, ws.final_state, entry, indices, T, S, K, max_blocks);
     if (launches) *launches = 3;
     return cudaGetLastError();
 }
@@ -182,13 +182,13 @@ cudaError_t launch_backtrace_blocked(const Workspace &ws, int32_t *indices, int6
 // torbi_b200_decode_checkpointed after a score-history kernel: the history already holds every P_t
 namespace {
 __global__ void gather_checkpoints_kernel(const float *__restrict__ history, const int32_t *__restrict__ frames_d,
-                                          const int64_t *__restrict__ item_row, float *__restrict__ checkpoints,
+                                          const int64_t *__restrict__ hist_row, float *__restrict__ checkpoints,
                                           int64_t B, int64_t S, int64_t every, int64_t rows) {
     const int64_t total = B * rows * S;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t s = i % S, k = (i / S) % rows, b = i / (S * rows);
         const int64_t t = (k + 1) * every;
-        if (t < frames_d[b]) checkpoints[i] = history[(item_row[b] + t) * S + s];
+        if (t < frames_d[b]) checkpoints[i] = history[(hist_row[b] + t) * S + s];
     }
 }
 }  // namespace
@@ -197,7 +197,7 @@ cudaError_t launch_gather_checkpoints(const ForwardArgs &a, cudaStream_t stream)
     const int64_t rows = (a.T - 1) / a.checkpoint_every;
     if (rows < 1) return cudaSuccess;
     gather_checkpoints_kernel<<<a.sm_count * 4, 256, 0, stream>>>(
-        reinterpret_cast<const float *>(a.ws.backptr), a.ws.frames, a.ws.item_row, a.checkpoints, a.B, a.S, a.checkpoint_every, rows);
+        reinterpret_cast<const float *>(a.ws.backptr), a.ws.frames, a.ws.hist_row, a.checkpoints, a.B, a.S, a.checkpoint_every, rows);
     return cudaGetLastError();
 }
 
@@ -241,8 +241,9 @@ template <int NK>
 __global__ void __launch_bounds__(kRecomputeThreads)
 backtrace_recompute_kernel(const float *__restrict__ history, const float *__restrict__ transition,
                            int64_t lda, const int32_t *__restrict__ frames_d,
-                           const int64_t *__restrict__ item_row, const int32_t *__restrict__ final_state,
-                           int32_t *__restrict__ indices, int64_t B, int64_t T, int S) {
+                           const int64_t *__restrict__ item_row, const int64_t *__restrict__ hist_row,
+                           const int32_t *__restrict__ final_state, int32_t *__restrict__ indices, int64_t B,
+                           int64_t T, int S) {
     const int lane = threadIdx.x % kWarp;
     const int64_t b = (int64_t)blockIdx.x * (kRecomputeThreads / kWarp) + threadIdx.x / kWarp;
     if (b >= B) return;
@@ -252,7 +253,7 @@ backtrace_recompute_kernel(const float *__restrict__ history, const float *__res
     int32_t *out = indices + row0;
     const int64_t out_len = T > 0 ? T : frames;       // T == 0: packed layout, the tail is the last frame alone
     for (int64_t t = frames - 1 + lane; t < out_len; t += kWarp) out[t] = last;      // viterbi.cpp:219-221
-    const float *hist = history + row0 * S;
+    const float *hist = history + hist_row[b] * S;
     int idx = last;
 
     if constexpr (NK > 0) {
@@ -331,20 +332,20 @@ cudaError_t launch_backtrace_recompute(const Workspace &ws, int32_t *indices, in
     const unsigned grid = (unsigned)((B + kRecomputeThreads / kWarp - 1) / (kRecomputeThreads / kWarp));
     if (S % 4 == 0 && S <= 128 * 4)
         backtrace_recompute_kernel<4><<<grid, kRecomputeThreads, 0, stream>>>(
-            history, ws.transition_pad, lda, ws.frames, ws.item_row, ws.final_state, indices, B, T, (int)S);
+            history, ws.transition_pad, lda, ws.frames, ws.item_row, ws.hist_row, ws.final_state, indices, B, T, (int)S);
     else if (S % 4 == 0 && S <= 128 * 12)
         backtrace_recompute_kernel<12><<<grid, kRecomputeThreads, 0, stream>>>(
-            history, ws.transition_pad, lda, ws.frames, ws.item_row, ws.final_state, indices, B, T, (int)S);
+            history, ws.transition_pad, lda, ws.frames, ws.item_row, ws.hist_row, ws.final_state, indices, B, T, (int)S);
     else
         backtrace_recompute_kernel<0><<<grid, kRecomputeThreads, 0, stream>>>(
-            history, ws.transition_pad, lda, ws.frames, ws.item_row, ws.final_state, indices, B, T, (int)S);
+            history, ws.transition_pad, lda, ws.frames, ws.item_row, ws.hist_row, ws.final_state, indices, B, T, (int)S);
     return cudaGetLastError();
 }
 
 cudaError_t launch_backtrace(const Workspace &ws, int32_t *indices, int64_t B, int64_t T,
                              int64_t S, cudaStream_t stream) {
     backtrace_kernel<<<(unsigned)B, kBacktraceThreads, 0, stream>>>(
-        ws.backptr, ws.frames, ws.item_row, ws.final_state, indices, T, S);
+        ws.backptr, ws.frames, ws.item_row, ws.hist_row, ws.final_state, indices, T, S);
     return cudaGetLastError();
 }
 

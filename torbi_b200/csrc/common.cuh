@@ -111,8 +111,10 @@ struct Workspace {
     int32_t *frames;        // (B,)  device copy of batch_frames
     int32_t *order;         // (B,)  items sorted by length, longest first
     int32_t *final_state;   // (B,)  argmax of the final forward scores
-    int64_t *item_row;      // (B,)  first row of each item in `observation` / history / backpointers / `indices`:
+    int64_t *item_row;      // (B,)  first row of each item in `observation` and `indices`:
                             //       b * T in the padded (B,T,S) layout, the caller's offsets in the packed one
+    int64_t *hist_row;      // (B,)  first row of each item in the score history / backpointers, which are always
+                            //       compact: sum(batch_frames) rows, item after item
     uint32_t *sync;         // scheduling / barrier words (zeroed per call)
     float *score[4];        // rotating forward-score buffers, (pad_batch, padded_sources) each
     float *block_max;       // 3 x (pad_batch, padded_sources / 16): max of each 16-state block of the rotating
@@ -146,8 +148,8 @@ inline bool workspace_has_history(uint32_t flags) { return !(flags & TORBI_B200_
 // `history` = the trailing region holds fp32 forward scores (4 bytes per (b,t,s): tiled kernel in
 // score-history mode, split / cluster kernels) rather than uint16 backpointers (2 bytes: wide and generic
 // kernels, tiled kernel in backpointer mode).  Everything before that region has the same layout
-// either way, so the region can be sized after the kernel has been chosen.  `rows` = rows of the
-// observation buffer: B * T in the padded layout, the packed total otherwise.
+// either way, so the region can be sized after the kernel has been chosen.  `rows` = rows of that
+// region: sum(batch_frames) (B * T as the upper bound when the lengths are not known yet).
 inline Workspace carve_workspace(void *base, int64_t B, int64_t rows, int64_t S, bool history) {
     Workspace w{};
     size_t off = 0;
@@ -161,6 +163,7 @@ inline Workspace carve_workspace(void *base, int64_t B, int64_t rows, int64_t S,
     w.order = static_cast<int32_t *>(take(sizeof(int32_t) * Bp));
     w.final_state = static_cast<int32_t *>(take(sizeof(int32_t) * B));
     w.item_row = static_cast<int64_t *>(take(sizeof(int64_t) * B));
+    w.hist_row = static_cast<int64_t *>(take(sizeof(int64_t) * B));
     w.sync = static_cast<uint32_t *>(take(sizeof(uint32_t) * kSyncWords));
     w.score[0] = static_cast<float *>(take(sizeof(float) * Bp * Sp));
     w.score[1] = static_cast<float *>(take(sizeof(float) * Bp * Sp));

@@ -56,7 +56,8 @@ struct ClusterParams {
     const float *transition;    // padded copy (SJ, LDP), -inf outside (S,S)
     const float *initial;       // (S,)
     const int32_t *frames;      // (B,)
-    const int64_t *item_row;    // (B,) first row of each item in observation / history
+    const int64_t *item_row;    // (B,) first row of each item in observation
+    const int64_t *hist_row;    // (B,) first row of each item in the (compact) history
     const int32_t *order;       // (Bpad,) items longest first, -1 = empty slot
     float *score0;              // 2 alternating buffers (Bpad, LDP), `score_stride` floats apart
     int64_t score_stride;
@@ -72,7 +73,7 @@ struct ClusterParams {
 size_t cluster_smem_bytes(int ldp) {
     return sizeof(float) * (kWarps * kSlots * kSlotFloats + TN * (ldp / 2 + 4)) +
            sizeof(float4) * (2 * kWarps * kReduceThreads + 2 * kReduceThreads) +
-           sizeof(int) * (4 * kMaxBatches * TM + kMaxBatches) + sizeof(u64) * 2 + 16;
+           sizeof(int) * (6 * kMaxBatches * TM + kMaxBatches) + sizeof(u64) * 2 + 16;
 }
 
 __device__ __forceinline__ u64 add2(u64 a, u64 b) {     // two fp32 adds (FADD2), IEEE rn
@@ -186,7 +187,8 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
     float4 *partial = reinterpret_cast<float4 *>(A_res + TN * LDA);   // [2][warp][160] per-warp maxima
     float4 *inbox = partial + 2 * kWarps * kReduceThreads;      // [2][160] the peer's reduced half
     int64_t *s_row = reinterpret_cast<int64_t *>(inbox + 2 * kReduceThreads);   // [kMaxBatches][TM] first row of the item
-    int *s_item = reinterpret_cast<int *>(s_row + kMaxBatches * TM);     // [kMaxBatches][TM]
+    int64_t *s_hrow = s_row + kMaxBatches * TM;                          // [kMaxBatches][TM] its first row in the history
+    int *s_item = reinterpret_cast<int *>(s_hrow + kMaxBatches * TM);    // [kMaxBatches][TM]
     int *s_frames = s_item + kMaxBatches * TM;                  // [kMaxBatches][TM]
     int *s_len = s_frames + kMaxBatches * TM;                   // [kMaxBatches] frames of the batch's longest item
     u64 *inbox_bar = reinterpret_cast<u64 *>(s_len + kMaxBatches);   // [2]
@@ -258,6 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
             s_item[idx] = item;
             s_frames[idx] = item >= 0 ? p.frames[item] : 0;
             s_row[idx] = item >= 0 ? p.item_row[item] : 0;
+            s_hrow[idx] = item >= 0 ? p.hist_row[item] : 0;
         }
         __syncthreads();
         if (tid < batches) s_len[tid] = s_frames[tid * TM];    // longest first
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
                     const int64_t e0 = s_row[b * TM + r] * S + c;
                     const float v = convert_observation<kFlags>(load_observation(p.observation, e0, p.obs_dtype)) + p.initial[c];
                     *dst0 = v;
-                    p.history[e0] = v;
+                    p.history[s_hrow[b * TM + r] * S + c] = v;
                 } else {
                     dst0[0] = 0.f;                               // padding stays finite, in both buffers
                     dst0[p.score_stride] = 0.f;
@@ -336,6 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
             float4 emit = make_float4(0.f, 0.f, 0.f, 0.f);
             const int fin_item = mine ? s_item[b * TM + fin_row] : -1;
             const int64_t fin_row0 = mine ? s_row[b * TM + fin_row] : 0;
+            const int64_t fin_hrow0 = mine ? s_hrow[b * TM + fin_row] : 0;
             const bool fin_live = mine && fin_item >= 0 && tau < s_frames[b * TM + fin_row] && j0 + fin_col < S;
             if (fin_live) {
                 if (p.frames_ready) wait_for_frame(tau);
@@ -441,7 +445,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
                         v.z = convert_observation<kFlags>(emit.z) + m.z;
                         v.w = convert_observation<kFlags>(emit.w) + m.w;
                         float *dst = p.score0 + (tau & 1) * p.score_stride + (row0 + fin_row) * LDP + col0;
-                        float *hist = p.history + (fin_row0 + tau) * S + col0;
+                        float *hist = p.history + (fin_hrow0 + tau) * S + col0;
                         if (col0 + 3 < S) {
                             *reinterpret_cast<float4 *>(dst) = v;
                             if (hist_vec) __stcs(reinterpret_cast<float4 *>(hist), v);
@@ -567,6 +571,7 @@ cudaError_t launch_forward_cluster(const ForwardArgs &a, cudaStream_t stream) {
     p.initial = a.initial;
     p.frames = a.ws.frames;
     p.item_row = a.ws.item_row;
+    p.hist_row = a.ws.hist_row;
     p.order = a.ws.order;
     p.score0 = a.ws.score[0];
     p.score_stride = a.ws.score[1] - a.ws.score[0];

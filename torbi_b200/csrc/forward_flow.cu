@@ -47,7 +47,8 @@ struct FlowParams {
     const float *transition;    // padded copy (SJ, LDP), -inf outside (S,S)
     const float *initial;       // (S,)
     const int32_t *frames;      // (B,)
-    const int64_t *item_row;    // (B,)
+    const int64_t *item_row;    // (B,) first row of each item in observation
+    const int64_t *hist_row;    // (B,) first row of each item in the (compact) backpointers
     const int32_t *order;       // (Bpad,) items longest first
     u64 *ll;                    // [2 sets][2 parities][LDP] tagged scores {fp32 bits, tag}
     uint16_t *backptr;          // (rows,S)
@@ -72,6 +73,20 @@ __device__ __forceinline__ u64 ld_ll(const u64 *p) {
 __device__ __forceinline__ unsigned tag_of(u64 w) { return (unsigned)(w >> 32); }
 __device__ __forceinline__ float value_of(u64 w) { return __uint_as_float((unsigned)w); }
 
+// -DTORBI_FLOW_WATCHDOG (debug builds only): a poll that spins for ~seconds reports what it saw and traps
+#ifdef TORBI_FLOW_WATCHDOG
+#define FLOW_WATCHDOG_DECL long long spins = 0;
+#define FLOW_WATCHDOG(word, q_)                                                                                \
+    if (++spins > (1ll << 24)) {                                                                               \
+        printf("flow watchdog: cta %d tid %d group %d expects tag %u, sees tag %u value %f\n", blockIdx.x,    \
+               threadIdx.x, (q_), tag, tag_of(word), value_of(word));                                          \
+        __trap();                                                                                              \
+    }
+#else
+#define FLOW_WATCHDOG_DECL
+#define FLOW_WATCHDOG(word, q_)
+#endif
+
 // the four scores of source group `q` (sources 4q .. 4q+3) once all carry `tag`; `valid` = how many of
 // the four are real states (the others read as 0: their transition entries are -inf)
 __device__ __forceinline__ float4 poll_group(const u64 *buf, int q, int valid, unsigned tag) {
@@ -79,16 +94,22 @@ __device__ __forceinline__ float4 poll_group(const u64 *buf, int q, int valid, u
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid == 4) {
         u64 w0, w1, w2, w3;
+        FLOW_WATCHDOG_DECL
         do {
             ld_ll2(p, w0, w1);
             ld_ll2(p + 2, w2, w3);
+            FLOW_WATCHDOG(tag_of(w0) != tag ? w0 : tag_of(w1) != tag ? w1 : tag_of(w2) != tag ? w2 : w3, q)
         } while (tag_of(w0) != tag || tag_of(w1) != tag || tag_of(w2) != tag || tag_of(w3) != tag);
         v = make_float4(value_of(w0), value_of(w1), value_of(w2), value_of(w3));
     } else {
         float e[4] = {0.f, 0.f, 0.f, 0.f};
         for (int x = 0; x < valid; ++x) {
             u64 w;
-            do { w = ld_ll(p + x); } while (tag_of(w) != tag);
+            FLOW_WATCHDOG_DECL
+            do {
+                w = ld_ll(p + x);
+                FLOW_WATCHDOG(w, q)
+            } while (tag_of(w) != tag);
             e[x] = value_of(w);
         }
         v = make_float4(e[0], e[1], e[2], e[3]);
@@ -149,6 +170,7 @@ __global__ void __launch_bounds__(kFlowThreads, 1) forward_flow_kernel(const Flo
         const int item = p.order[n];
         const int frames = p.frames[item];
         const int64_t row0 = p.item_row[item];
+        const int64_t hrow0 = p.hist_row[item];
         u64 *set = p.ll + (size_t)(n & 1) * 2 * LDP;
 
         // ---- t = 0: P_0[j] = obs[0][j] + initial[j]   (viterbi.cpp:72-76), own destination states ----
@@ -267,7 +289,7 @@ __global__ void __launch_bounds__(kFlowThreads, 1) forward_flow_kernel(const Flo
             }
             __syncthreads();
             if (tid < rows)
-                p.backptr[(row0 + t) * S + j_begin + tid] = (uint16_t)min(arg[tid], S - 1);
+                p.backptr[(hrow0 + t) * S + j_begin + tid] = (uint16_t)min(arg[tid], S - 1);
         }
 
         // ---- every CTA waits for the final scores (this is what orders the reuse of the buffer set);
@@ -370,6 +392,7 @@ cudaError_t launch_forward_flow(const ForwardArgs &a, cudaStream_t stream) {
     p.initial = a.initial;
     p.frames = a.ws.frames;
     p.item_row = a.ws.item_row;
+    p.hist_row = a.ws.hist_row;
     p.order = a.ws.order;
     p.ll = reinterpret_cast<u64 *>(a.ws.score[0]);
     p.backptr = a.ws.backptr;

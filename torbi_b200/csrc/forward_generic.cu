@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(kGenericThreads)
 forward_generic_kernel(const float *__restrict__ observation, int obs_dtype,
                        float *__restrict__ checkpoints, int64_t checkpoint_every,
                        const int32_t *__restrict__ frames_d, const int64_t *__restrict__ item_row,
+                       const int64_t *__restrict__ hist_row,
                        const float *__restrict__ transition,
                        const float *__restrict__ initial, float *score0, float *score1,
                        uint16_t *__restrict__ backptr, float *__restrict__ posterior,
@@ -35,7 +36,7 @@ forward_generic_kernel(const float *__restrict__ observation, int obs_dtype,
     const int64_t b = blockIdx.x;
     const int frames = frames_d[b];
     const int64_t obs0 = item_row[b] * S;               // element offset of this sequence
-    uint16_t *bp = backptr + obs0;
+    uint16_t *bp = backptr + hist_row[b] * S;
     float *cur = scores_in_smem ? smem_scores : score0 + b * score_stride;
     float *nxt = scores_in_smem ? smem_scores + S : score1 + b * score_stride;
 
@@ -133,7 +134,7 @@ static cudaError_t launch_generic_t(const ForwardArgs &a, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
     }
     kernel<<<(unsigned)a.B, kGenericThreads, smem, stream>>>(
-        a.observation, a.obs_dtype, a.checkpoints, a.checkpoint_every, a.ws.frames, a.ws.item_row, a.transition, a.initial, a.ws.score[0], a.ws.score[1],
+        a.observation, a.obs_dtype, a.checkpoints, a.checkpoint_every, a.ws.frames, a.ws.item_row, a.ws.hist_row, a.transition, a.initial, a.ws.score[0], a.ws.score[1],
         a.ws.backptr, a.posterior, a.ws.final_state, a.checkpoints ? (a.T - 1) / a.checkpoint_every : 0, (int)a.S, padded_sources(a.S), in_smem);
     return cudaGetLastError();
 }

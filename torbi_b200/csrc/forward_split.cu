@@ -78,7 +78,7 @@ template <typename Shape>
 size_t smem_bytes(int ldp) {
     return sizeof(float) * (ring_floats<Shape>() + kTileCells + kWarps * kTileCells +
                             (Shape::kResident ? Shape::TN * (ldp + 4) : 0)) +
-           sizeof(int) * 4 * Shape::TM + sizeof(u64) * 2 * Shape::NSTAGE;
+           sizeof(int) * 6 * Shape::TM + sizeof(u64) * 2 * Shape::NSTAGE;
 }
 
 __device__ __forceinline__ u64 add2(u64 a, u64 b) {     // two fp32 adds (FADD2), IEEE rn
@@ -142,7 +142,8 @@ struct SplitParams {
     const float *transition;    // padded copy (SJ, LDP), -inf outside (S,S)
     const float *initial;       // (S,)
     const int32_t *frames;      // (B,)
-    const int64_t *item_row;    // (B,) first row of each item in observation / history
+    const int64_t *item_row;    // (B,) first row of each item in observation
+    const int64_t *hist_row;    // (B,) first row of each item in the (compact) history
     const int32_t *order;       // (Bpad,) items longest first, -1 = empty slot
     float *score0;              // 3 rotating buffers (Bpad, LDP), `score_stride` floats apart
     int64_t score_stride;
@@ -194,7 +195,8 @@ __global__ void __launch_bounds__(kThreads, 1) forward_split_kernel(const SplitP
     float *A_res = partial + kWarps * TM * TN;                  // resident shape: [TN][LDP + 4] transition block
     const int LDA = p.LDP + 4;                                  // rows 4 banks apart, like the ring's
     int64_t *slot_row = reinterpret_cast<int64_t *>(A_res + (Shape::kResident ? TN * LDA : 0));   // [TM] first row of the slot's item
-    int *slot_item = reinterpret_cast<int *>(slot_row + TM);
+    int64_t *slot_hrow = slot_row + TM;                         // [TM] its first row in the history
+    int *slot_item = reinterpret_cast<int *>(slot_hrow + TM);
     int *slot_frames = slot_item + TM;
     u64 *full_bar = reinterpret_cast<u64 *>(slot_frames + TM);  // [NSTAGE] one arrival per thread: its copies landed
     u64 *empty_bar = full_bar + NSTAGE;                         // [NSTAGE] one arrival per warp: done reading
@@ -268,6 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_split_kernel(const SplitP
             slot_item[tid] = item;
             slot_frames[tid] = item >= 0 ? p.frames[item] : 0;
             slot_row[tid] = item >= 0 ? p.item_row[item] : 0;
+            slot_hrow[tid] = item >= 0 ? p.hist_row[item] : 0;
         }
         __syncthreads();
         const int batch_frames = slot_frames[0];        // longest first
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_split_kernel(const SplitP
                     if (item >= 0 && c < S) {
                         const float v = convert_observation<kFlags>(load_observation(p.observation, obs0 + c, p.obs_dtype)) + p.initial[c];
                         dst0[c] = v;
-                        p.history[obs0 + c] = v;
+                        p.history[slot_hrow[r] * S + c] = v;
                     } else {
                         dst0[c] = 0.f;                   // padding stays finite, in all buffers
                         dst1[c] = 0.f;
@@ -480,7 +483,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_split_kernel(const SplitP
                 if (col < S && slot_item[r] >= 0) {                       // padding never changes
                     const int64_t off = (row0 + r) * LDP + col;
                     const bool live = t < slot_frames[r];
-                    float *hist = live ? p.history + (slot_row[r] + t) * S + col : nullptr;
+                    float *hist = live ? p.history + (slot_hrow[r] + t) * S + col : nullptr;
                     if (col + 3 < S) {
                         const float4 v = live ? *reinterpret_cast<const float4 *>(tile + r * TN + c4 * 4)
                                               : __ldcg(reinterpret_cast<const float4 *>(P_cur + off));
@@ -571,6 +574,7 @@ static cudaError_t launch_split_t(const ForwardArgs &a, cudaStream_t stream) {
     p.initial = a.initial;
     p.frames = a.ws.frames;
     p.item_row = a.ws.item_row;
+    p.hist_row = a.ws.hist_row;
     p.order = a.ws.order;
     p.score0 = a.ws.score[0];
     p.score_stride = a.ws.score[1] - a.ws.score[0];

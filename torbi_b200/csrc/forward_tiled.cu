@@ -79,7 +79,7 @@ constexpr int stage_floats(int M) { return (tile_rows(M) + TN) * LDS_; }
 constexpr size_t smem_bytes(int M) {
     return sizeof(float) * (NSTAGE * stage_floats(M) + 2 * tile_rows(M) * TN)  // ring + emission/score + max tiles
            + sizeof(uint16_t) * tile_rows(M) * TN                              // winning chunk -> backpointer tile
-           + sizeof(int) * 6 * tile_rows(M)                                    // per-slot item id, length, first row (int64); banded: outside max / index
+           + sizeof(int) * 8 * tile_rows(M)                                    // per-slot item id, length, first rows (2 x int64); banded: outside max / index
            + sizeof(u64) * 2 * NSTAGE;                                         // full / empty mbarrier per ring slot
 }
 static_assert(smem_bytes(4) <= 227 * 1024, "shared memory budget");
@@ -138,7 +138,8 @@ struct TiledParams {
     const float *transition;    // padded copy (SJ, LDP), -inf outside (S,S)
     const float *initial;       // (S,)
     const int32_t *frames;      // (B,)
-    const int64_t *item_row;    // (B,) first row of each item in observation / history / backptr
+    const int64_t *item_row;    // (B,) first row of each item in observation
+    const int64_t *hist_row;    // (B,) first row of each item in history / backptr (compact: sum(frames) rows)
     const int32_t *order;       // (Bpad,) items longest first, -1 = empty slot
     float *score0;              // 3 rotating buffers (Bpad, LDP), `score_stride` floats apart;
     int64_t score_stride;       // row = position in `order`
@@ -291,7 +292,8 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
     // once its async copies for the stage have landed; empty[slot] one per warp once it has
     // finished reading the stage.  Warps may drift apart by up to a stage.
     int64_t *slot_row = reinterpret_cast<int64_t *>(out_i + TM);       // [TM] first row of the slot's item
-    u64 *full_bar = reinterpret_cast<u64 *>(slot_row + TM);            // [NSTAGE]
+    int64_t *slot_hrow = slot_row + TM;                                // [TM] its first row in the history / backpointers
+    u64 *full_bar = reinterpret_cast<u64 *>(slot_hrow + TM);           // [NSTAGE]
     u64 *empty_bar = full_bar + NSTAGE;                                // [NSTAGE]
     if (threadIdx.x == 0) {
         for (int k = 0; k < NSTAGE; ++k) {
@@ -378,6 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
             slot_item[tid] = item;
             slot_frames[tid] = item >= 0 ? p.frames[item] : 0;
             slot_row[tid] = item >= 0 ? p.item_row[item] : 0;
+            slot_hrow[tid] = item >= 0 ? p.hist_row[item] : 0;
         }
         __syncthreads();
         const int batch_frames = slot_frames[0];        // longest first
@@ -396,7 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                     if (item >= 0 && c < S) {
                         const float v = convert_observation<kFlags>(load_observation(p.observation, obs0 + c, p.obs_dtype)) + p.initial[c];
                         dst0[c] = v;
-                        if (kHist) p.history[obs0 + c] = v;
+                        if (kHist) p.history[slot_hrow[r] * S + c] = v;
                     } else {
                         dst0[c] = 0.f;                   // padding stays finite, in all buffers
                         dst1[c] = 0.f;
@@ -666,7 +669,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                     const int64_t off = (row0 + r) * LDP + col;
                     const bool live = t < slot_frames[r];
                     // score-history mode: P_t of live rows also goes to the (B,T,S) history (streaming store)
-                    float *hist = (kHist && live) ? p.history + (slot_row[r] + t) * S + col : nullptr;
+                    float *hist = (kHist && live) ? p.history + (slot_hrow[r] + t) * S + col : nullptr;
                     if (col + 3 < S) {
                         v = live ? *reinterpret_cast<const float4 *>(tile + r * TN + c4 * 4)
                                  : __ldcg(reinterpret_cast<const float4 *>(P_cur + off));
@@ -721,14 +724,14 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tiled_kernel(const TiledP
                 for (int idx = tid; idx < TM * (TN / 8); idx += kThreads) {
                     const int r = idx / (TN / 8), c8 = idx % (TN / 8);
                     if (t < slot_frames[r] && j0 + c8 * 8 < S)
-                        *reinterpret_cast<uint4 *>(p.backptr + (slot_row[r] + t) * S + j0 + c8 * 8) =
+                        *reinterpret_cast<uint4 *>(p.backptr + (slot_hrow[r] + t) * S + j0 + c8 * 8) =
                             *reinterpret_cast<const uint4 *>(bp_tile + r * TN + c8 * 8);
                 }
             } else {
                 for (int idx = tid; idx < TM * TN; idx += kThreads) {
                     const int r = idx / TN, c = idx % TN;
                     if (t < slot_frames[r] && j0 + c < S)
-                        p.backptr[(slot_row[r] + t) * S + j0 + c] = bp_tile[idx];
+                        p.backptr[(slot_hrow[r] + t) * S + j0 + c] = bp_tile[idx];
                 }
             }
             }   // !kHist
@@ -831,6 +834,7 @@ static cudaError_t launch_tiled_t(const ForwardArgs &a, cudaStream_t stream) {
     p.initial = a.initial;
     p.frames = a.ws.frames;
     p.item_row = a.ws.item_row;
+    p.hist_row = a.ws.hist_row;
     p.order = a.ws.order;
     p.score0 = a.ws.score[0];
     p.score_stride = a.ws.score[1] - a.ws.score[0];

@@ -37,7 +37,8 @@ struct WideParams {
     const float *transition;    // padded copy (SJ, LDP), -inf outside (S,S)
     const float *initial;       // (S,)
     const int32_t *frames;      // (B,)
-    const int64_t *item_row;    // (B,) first row of each item in observation / backptr
+    const int64_t *item_row;    // (B,) first row of each item in observation
+    const int64_t *hist_row;    // (B,) first row of each item in the (compact) backpointers
     const int32_t *order;       // (Bpad,) items longest first
     float *score0;              // 2 alternating buffers (Bpad, LDP), `score_stride` floats apart
     int64_t score_stride;
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
     float *Ps = smem;                                    // [BC][LDP] previous scores
     float *As = smem + BC * LDP;                         // [resident_rows][LDP] transition slice
     __shared__ int slot_item[BC], slot_frames[BC];
-    __shared__ int64_t slot_row[BC];
+    __shared__ int64_t slot_row[BC], slot_hrow[BC];
     __shared__ int ready_shared;
 
     const int tid = threadIdx.x, lane = tid % kWarp, warp = tid / kWarp;
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
             slot_item[tid] = item;
             slot_frames[tid] = item >= 0 ? p.frames[item] : 0;
             slot_row[tid] = item >= 0 ? p.item_row[item] : 0;
+            slot_hrow[tid] = item >= 0 ? p.hist_row[item] : 0;
         }
         __syncthreads();
         const int group_frames = slot_frames[0];         // longest first
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
                         const bool live = t < slot_frames[bb];
                         P_new[(int64_t)bb * LDP + j] = live ? e + v : e;         // viterbi.cpp:102 / carried
                         if (live) {
-                            p.backptr[(slot_row[bb] + t) * S + j] = (uint16_t)min(arg, S - 1);
+                            p.backptr[(slot_hrow[bb] + t) * S + j] = (uint16_t)min(arg, S - 1);
                             if (p.checkpoints && t % p.checkpoint_every == 0)
                                 p.checkpoints[((int64_t)slot_item[bb] * p.ck_rows + (t / p.checkpoint_every - 1)) * S + j] = e + v;
                         }
@@ -344,6 +346,7 @@ cudaError_t launch_forward_wide(const ForwardArgs &a, cudaStream_t stream) {
     p.initial = a.initial;
     p.frames = a.ws.frames;
     p.item_row = a.ws.item_row;
+    p.hist_row = a.ws.hist_row;
     p.order = a.ws.order;
     p.score0 = a.ws.score[0];
     p.score_stride = a.ws.score[1] - a.ws.score[0];

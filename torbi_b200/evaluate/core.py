@@ -42,8 +42,8 @@ def synthetic_dataset(name: str, root=None, files: int = 64, states: int = _metr
         contour = contour.clamp(5, states - 6)
         voiced = (torch.rand(frames, generator=g) < 0.97).float()
         voiced = (torch.nn.functional.avg_pool1d(voiced[None, None], 9, 1, 4)[0, 0] > 0.8)   # unvoiced in stretches
-        sharp = torch.where(voiced, 0.08, 1e-4)[:, None]
-        logits = -sharp * (bins[None] - contour[:, None]) ** 2 + torch.randn(frames, states, generator=g) * 1.5
+        sharp = torch.where(voiced, 0.5, 1e-4)[:, None]
+        logits = -sharp * (bins[None] - contour[:, None]) ** 2 + torch.randn(frames, states, generator=g)
         stem = f'{name}-{i:05d}'
         torch.save(torch.log_softmax(logits, dim=-1).to(dtype), cache / f'{stem}.pt')
         torch.save(contour.round().to(torch.int32), cache / f'{stem}.truth.pt')
