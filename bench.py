@@ -60,7 +60,7 @@ def parse_args():
     parser.add_argument('--cpu-seconds', type=float, default=None,
                         help='CPU work per reference step / cpu_baseline sample (default: sized automatically)')
     parser.add_argument('--no-cpu-baseline', action='store_true')
-    parser.add_argument('--kernel', default='auto', choices=['auto', 'generic', 'tiled', 'wide', 'split', 'cluster'])
+    parser.add_argument('--kernel', default='auto', choices=['auto', 'generic', 'tiled', 'wide', 'split', 'cluster', 'flow'])
     parser.add_argument('--no-strong', action='store_true', help='skip the strong-scaling leg (N > 1)')
     parser.add_argument('--no-configs', action='store_true', help='skip BASELINE configs 1 / 3 / 5 (N = 1)')
     parser.add_argument('--skip-config3', action='store_true')
@@ -528,7 +528,7 @@ def bench_graft(args):
     obs, frames, A, init = make_workload(args, device, 1234 + rank)
     flags = _ffi.EPS_FLOOR | _ffi.TIME_KERNELS
     flags |= {'auto': 0, 'generic': _ffi.FORCE_GENERIC, 'tiled': _ffi.FORCE_TILED, 'wide': _ffi.FORCE_WIDE,
-              'split': _ffi.FORCE_SPLIT, 'cluster': _ffi.FORCE_CLUSTER}[args.kernel]
+              'split': _ffi.FORCE_SPLIT, 'cluster': _ffi.FORCE_CLUSTER, 'flow': _ffi.FORCE_FLOW}[args.kernel]
     flags |= {0: 0, 16: _ffi.TILE_ROWS_16, 32: _ffi.TILE_ROWS_32, 64: _ffi.TILE_ROWS_64}[args.tile_rows]
     if args.banded:
         flags |= _ffi.BANDED

@@ -457,6 +457,21 @@ def test_flow_kernel_matches_oracle(shape, oracle):
         assert np.array_equal(again, want_idx)
 
 
+def test_flow_kernel_runs_of_one_frame_sequences(oracle):
+    """Sequences follow each other without a grid barrier and two buffer sets alternate.  Runs of
+    one-frame items (no recursion step, hence no CTA barrier of the step loop) between longer ones are
+    the case where a fast CTA could reuse a set while a slow one still reads the final scores in it."""
+    B, T, S = 60, 9, 1440
+    obs, frames, A, init = random_problem(777, B, T, S, quant=2)
+    frames[:] = 1
+    frames[::7] = [9, 3, 2, 8, 1, 5, 2, 3, 1][:len(frames[::7])]
+    want_idx, want_post = oracle.c_decode(obs, frames, A, init, exact_scan=False, want_posterior=True)
+    for _ in range(5):
+        indices, posterior = gpu_decode(obs, frames, A, init, flags=_ffi.FORCE_FLOW)
+        assert np.array_equal(indices, want_idx)
+        assert np.array_equal(bits(posterior), bits(want_post))
+
+
 def test_flow_kernel_is_what_single_sequences_get(oracle):
     """BASELINE config 1 shape (S=1440, B=1, T=2000, uniform transition / initial) through the selector."""
     rng = np.random.default_rng(1)

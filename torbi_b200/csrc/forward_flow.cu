@@ -21,8 +21,9 @@
 //     publish, while the scores are on their way to the other SMs: only warps whose partial maximum
 //     equals the final one re-evaluate their candidates (the same single fp32 add, so equality is exact).
 // Sequences are taken one after the other (longest first); tags keep counting across sequences and two
-// buffer sets alternate, so no barrier separates them either: every CTA polls the final scores of a
-// sequence before it starts the next one, which is what makes reusing a set two sequences later safe.
+// buffer sets alternate, so no grid barrier separates them either: every CTA polls the final scores of a
+// sequence (and meets at a CTA barrier) before it publishes anything for the next one, which is what
+// makes reusing a set two sequences later safe.
 // Stores uint16 backpointers like forward_wide (backtrace.cu chases them, blocked for long sequences).
 #include <algorithm>
 
@@ -314,6 +315,10 @@ __global__ void __launch_bounds__(kFlowThreads, 1) forward_flow_kernel(const Flo
                     }
                 }
             }
+            // EVERY thread of the CTA has its final scores before any thread publishes for the next sequence:
+            // the next sequence's first publish is what lets the other CTAs run ahead and reuse this set
+            // (with a one-frame sequence in between there is no other barrier on that path)
+            __syncthreads();
             if (writer) {
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
