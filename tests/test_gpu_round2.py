@@ -423,7 +423,7 @@ def test_packed_host_entry_and_validation(oracle):
     with pytest.raises(ValueError, match='overlap'):
         torbi_b200.decode_packed(cuda(packed), t(bad), t(frames), cuda(A), cuda(init))
     bad = item_row.copy()
-    bad[int(np.argmax(item_row))] = rows - 1                     # runs off the end
+    bad[int(np.argmax(item_row))] = rows                         # runs off the end
     with pytest.raises(ValueError, match='leave the buffer'):
         torbi_b200.decode_packed(cuda(packed), t(bad), t(frames), cuda(A), cuda(init))
 

@@ -69,9 +69,9 @@ def test_kernel_plan_host_logic():
     assert plan([2000] * 64, 2000, 1440) == 'forward_split'                # the per-GPU share of 512 over 8 GPUs
     assert plan([2000] * 128, 2000, 1440, _ffi.BACKPOINTERS) == 'forward_tiled_16'   # (no split kernel in that mode)
     assert plan([2000], 2000, 1440) == 'forward_flow'                      # config 1
-    assert plan([1000000], 1000000, 4096) == 'forward_flow'                # config 5
-    assert plan([2000] * 8, 2000, 1440) == 'forward_flow'                  # (sequences one after the other)
-    assert plan([2000] * 8, 2000, 1440, _ffi.FORCE_WIDE) == 'forward_wide'
+    assert plan([1000000], 1000000, 4096) == 'forward_wide'                # config 5
+    assert plan([2000], 2000, 4096, _ffi.FORCE_FLOW) == 'forward_flow'
+    assert plan([2000] * 8, 2000, 1440) == 'forward_wide'                  # a few sequences in lockstep
     assert plan([2000] * 32, 2000, 1440) == 'forward_split'
     assert plan(full, 2000, 1440, _ffi.FORCE_SPLIT) == 'forward_split'
     assert plan(full, 2000, 1440, _ffi.FORCE_SPLIT | _ffi.BACKPOINTERS) is None
@@ -381,7 +381,7 @@ def test_planned_workspace_follows_the_kernel_choice():
 
     upper = lib.torbi_b200_workspace_bytes(1, 1_000_000, 4096, 0)
     exact = planned([1_000_000], 1_000_000, 4096)
-    assert plan([1_000_000], 1_000_000, 4096) == 'forward_flow'
+    assert plan([1_000_000], 1_000_000, 4096) == 'forward_wide'
     assert upper - exact == 2 * 1_000_000 * 4096 and exact < 8.3e9
     assert planned([2000] * 512, 2000, 1440) == lib.torbi_b200_workspace_bytes(512, 2000, 1440, 0)
     assert planned([2000] * 64, 2000, 1440, _ffi.FORCE_CLUSTER) == lib.torbi_b200_workspace_bytes(64, 2000, 1440, 0)
