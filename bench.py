@@ -365,6 +365,23 @@ def other_configs(lib, device, local, peaks, sm_count, barrier, args):
             'backtrace_ms': r['back_ms'],
             'frac_fp32_maxplus': 2.0 * S * S * timesteps / (r['fwd_ms'] * 1e-3) / 1e12 / fp32_peak(sm_count, peaks),
             'peak_hbm_gb': r['peak_hbm_gb'], 'clocks': r['clocks'], 'checksum': r['checksum']}
+        if r['kernel'] == 'forward_wide' and obs.shape[0] == 1:
+            # one sequence through the wide kernel: a step = the grid barrier (1.25 us measured for 148 CTAs,
+            # profiles/r02_microbench_sync.txt) + the longer of the scan and the L2 stream of the transition rows
+            # shared memory cannot hold (13.7 TB/s measured L2->SM stream rate, same file)
+            clk = peaks['sm_max_mhz'] * 1e6
+            ldp = -(-S // 96) * 96
+            rows = -(-S // sm_count)
+            resident = min(rows, (200 * 1024 - 4 * ldp) // (4 * ldp))
+            streamed_bytes = (rows - resident) * ldp * 4.0 * -(-S // rows)
+            floor_us = 1.25 + 1e6 * max(S * S / sm_count / 64.0 / clk, streamed_bytes / 13.7e12)
+            us = 1e3 * r['fwd_ms'] / max(1, timesteps - 1)
+            out[name]['latency_bound'] = {
+                'us_per_step': us, 'floor_us_per_step': floor_us, 'frac': floor_us / us,
+                'streamed_bytes_per_step': streamed_bytes, 'l2_stream_gbs': streamed_bytes / (us * 1e-6) / 1e9,
+                'note': 'single-sequence recursion is latency / L2-stream bound, not FP32 bound: floor = grid barrier '
+                        '(1.25 us measured) + max(scan at 64 cells/clk/SM, L2 stream of the non-resident transition rows at '
+                        'the measured 13.7 TB/s)'}
         if r['kernel'] == 'forward_flow':
             # one sequence: a timestep cannot start before the previous one's scores have crossed L2.  Floor of
             # a step = L2 store + L2 load latency (2 x ~250 cycles, B300_MICROARCH.md "L2 hit latency") + the
