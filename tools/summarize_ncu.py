@@ -30,6 +30,8 @@ KEEP = [
     'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
     'sm__cycles_elapsed.avg', 'sm__cycles_active.avg',
     'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+    'lts__t_bytes.sum', 'lts__t_sectors_srcunit_tex_op_read.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+    'l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum',
 ]
 
 

@@ -27,7 +27,7 @@ from .viterbi import decode, decode_packed
 
 __all__ = [
     'from_probabilities', 'from_file', 'from_file_to_file', 'from_files_to_files',
-    'from_dataloader', 'save', 'save_masked']
+    'from_dataloader', 'save', 'save_masked', 'release_pinned_buffers']
 
 Gpu = Optional[Union[int, str, Sequence[int]]]
 
@@ -551,8 +551,9 @@ def _from_files_native(input_files, sizes, mapping, transition, initial, log_pro
         numel = max(len(batch) * int(sizes[batch[0]]) for batch in batches) // 4 + 1
     pin = torch.cuda.is_available()
     free: queue.Queue = queue.Queue()
-    for _ in range(depth + 1):
-        free.put(torch.empty(numel, dtype=torch.float32, pin_memory=pin))
+    ring = _take_pinned_buffers(depth + 1, numel, pin)
+    for buffer in ring:
+        free.put(buffer)
     ready: queue.Queue = queue.Queue(maxsize=depth)
     done = object()
     stop = threading.Event()          # set when the consumer gives up: the producer must not block for ever
@@ -652,8 +653,40 @@ def _from_files_native(input_files, sizes, mapping, transition, initial, log_pro
         stop.set()
         producer.join()
         saver.shutdown(wait=True)
+        _return_pinned_buffers(ring)
         if bar is not None:
             bar.close()
+
+
+# Page-locking 3 x 512 MB takes ~0.4 s -- as long as decoding a thousand files -- so the ring buffers of the
+# file pipeline are kept between calls (release_pinned_buffers() frees them).
+_PINNED_POOL: List[torch.Tensor] = []
+_PINNED_LOCK = threading.Lock()
+
+
+def _take_pinned_buffers(count, numel, pin):
+    taken = []
+    with _PINNED_LOCK:
+        for buffer in list(_PINNED_POOL):
+            if len(taken) < count and buffer.numel() >= numel and buffer.is_pinned() == pin:
+                _PINNED_POOL.remove(buffer)
+                taken.append(buffer)
+    while len(taken) < count:
+        taken.append(torch.empty(numel, dtype=torch.float32, pin_memory=pin))
+    return taken
+
+
+def _return_pinned_buffers(buffers, keep=6):
+    with _PINNED_LOCK:
+        _PINNED_POOL.extend(buffers)
+        _PINNED_POOL.sort(key=lambda buffer: -buffer.numel())
+        del _PINNED_POOL[keep:]
+
+
+def release_pinned_buffers():
+    """Free the page-locked ring buffers the file pipeline keeps between calls."""
+    with _PINNED_LOCK:
+        _PINNED_POOL.clear()
 
 
 # counters of the last file pipelines (frames seen / re-checked by the device chunker, pieces decoded)

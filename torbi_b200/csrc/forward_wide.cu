@@ -184,6 +184,8 @@ __global__ void __launch_bounds__(kWideThreads, 1) forward_wide_kernel(const Wid
                 int arg_b[BW];
                 // the scan, parametrised on where the transition row lives: resident rows are
                 // read with LDS, the rest of the slice streams from L2
+                // (issuing 8 loads per lane ahead of the scan on streamed rows was measured SLOWER: 10.8 vs
+                // 8.4 us per step at S = 4096, profiles/r02_wide_kernel_notes.txt)
                 auto scan_row = [&](auto load_a) {
                     for (int q = lane; q < LDP / 4; q += kWarp) {
                         const float4 a = load_a(q);
