@@ -15,7 +15,12 @@ if [ "$1" = build ]; then
   ls -la "$variant"
   exit 0
 fi
-summary() { grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard|^ok " | sort | uniq -c | sort -rn | head -${2:-12}; }
+summary() {
+  tee /tmp/sanitizer_raw.txt > /dev/null
+  echo "decodes checked against the oracle: $(grep -c '^ok ' /tmp/sanitizer_raw.txt)"
+  grep -E "ERROR SUMMARY|RACECHECK SUMMARY" /tmp/sanitizer_raw.txt | sort | uniq -c
+  grep -E "hazard|Invalid|Uninitialized|Barrier error" /tmp/sanitizer_raw.txt | sed 's/+0x[0-9a-f]*//; s/=========//' | sort | uniq -c | sort -rn | head -${2:-6}
+}
 for tool in ${TOOLS:-memcheck synccheck racecheck}; do
   echo "== $tool, shipped library"
   compute-sanitizer --tool $tool --print-limit 5 python tests/sanitizer_workload.py 2>&1 | summary

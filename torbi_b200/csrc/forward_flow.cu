@@ -194,7 +194,10 @@ __device__ __forceinline__ void reduce_rows(float (&v)[kChunk], int (&ix)[kChunk
     }
 }
 
-template <int KQ, int RR>
+// kAllReg: every row of the CTA's transition slice sits in registers (R <= RR): the shared-memory and streamed
+// row paths -- and the per-thread arrays they index at run time, which ptxas keeps in local memory -- are
+// compiled out
+template <int KQ, int RR, bool kAllReg>
 __global__ void __launch_bounds__(kFlowThreads, 1) forward_flow_kernel(const FlowParams p) {
     // dynamic shared memory: per-warp partial maxima of every row, double buffered (ordered score bits and
     // lowest source index), then the shared-memory rows of the transition slice
@@ -232,14 +235,14 @@ __global__ void __launch_bounds__(kFlowThreads, 1) forward_flow_kernel(const Flo
                 a_reg[r][k] = __ldg(reinterpret_cast<const ulonglong2 *>(p.transition + (int64_t)(j_begin + r) * LDP) + q[k]);
         }
     }
-    const int smem_rows = max(0, min(p.smem_rows, rows - RR));
+    const int smem_rows = kAllReg ? 0 : max(0, min(p.smem_rows, rows - RR));
     for (int idx = tid; idx < smem_rows * (LDP / 4); idx += kFlowThreads) {
         const int r = idx / (LDP / 4), c = idx % (LDP / 4);
         reinterpret_cast<float4 *>(As + r * LDP)[c] =
             __ldg(reinterpret_cast<const float4 *>(p.transition + (int64_t)(j_begin + RR + r) * LDP) + c);
     }
     const int first_streamed = RR + smem_rows;
-    const int ns = max(0, rows - first_streamed);        // rows streamed from L2 every step
+    const int ns = kAllReg ? 0 : max(0, rows - first_streamed);        // rows streamed from L2 every step
     const int stream_stride = ns > 1 ? max(1, smem_rows / (ns - 1)) : smem_rows + 1;
     ulonglong2 sbuf0[KQ], sbuf1[KQ];
     auto load_streamed = [&](int i, ulonglong2 *dst) {
@@ -300,11 +303,13 @@ __global__ void __launch_bounds__(kFlowThreads, 1) forward_flow_kernel(const Flo
             //      every thread polled its own 32 bytes instead, the spinning alone would draw more than half
             //      of the L2 bandwidth (148 SMs x 8 S bytes per ~500-cycle round) and every load on the chip --
             //      the publishes, the emissions, the streamed transition rows -- would queue behind it ----
-            if (warp_active) {
-                // rows of the transition slice that neither registers nor shared memory hold stream from L2:
-                // two rows in flight, requested before the wait (they do not depend on the scores)
-                if (ns > 0) load_streamed(0, sbuf0);
-                if (ns > 1) load_streamed(1, sbuf1);
+            if constexpr (!kAllReg) {
+                if (warp_active) {
+                    // rows of the transition slice that neither registers nor shared memory hold stream from L2:
+                    // two rows in flight, requested before the wait (they do not depend on the scores)
+                    if (ns > 0) load_streamed(0, sbuf0);
+                    if (ns > 1) load_streamed(1, sbuf1);
+                }
             }
             FPROF_MARK(4)
             if (p.gate && tid < p.NC) {
@@ -375,6 +380,7 @@ __global__ void __launch_bounds__(kFlowThreads, 1) forward_flow_kernel(const Flo
                 for (int i = 0; i < kChunk; ++i) { sv[i] = -INFINITY; si[i] = 0x7fffffff; }
                 int retired = 0;
                 auto retire = [&]() {
+                    if constexpr (kAllReg) return;
                     if (retired >= ns) return;
                     float m;
                     int first;
@@ -412,7 +418,7 @@ __global__ void __launch_bounds__(kFlowThreads, 1) forward_flow_kernel(const Flo
                     }
                 }
                 // shared-memory rows
-                for (int rs0 = 0; rs0 < smem_rows; rs0 += kChunk) {
+                for (int rs0 = 0; !kAllReg && rs0 < smem_rows; rs0 += kChunk) {
                     float cv[kChunk];
                     int ci[kChunk];
 #pragma unroll
@@ -430,7 +436,7 @@ __global__ void __launch_bounds__(kFlowThreads, 1) forward_flow_kernel(const Flo
                     }
                     store_chunk(RR + rs0, min(kChunk, smem_rows - rs0), cv, ci);
                 }
-                while (retired < ns) retire();
+                while (!kAllReg && retired < ns) retire();
                 FPROF_MARK(1)
             }
             __syncthreads();        // the only CTA barrier of a step
@@ -446,7 +452,9 @@ __global__ void __launch_bounds__(kFlowThreads, 1) forward_flow_kernel(const Flo
                         // every thread's candidate of this row: 32 x active_warps keys, a few per lane, then a butterfly
                         const u64 *keys = cand + ((size_t)(steps_done & 1u) * R + r) * kFlowThreads + lane;
                         u64 key = 0;
-                        for (int w = 0; w < active_warps; ++w) key = max(key, keys[w * kWarp]);
+#pragma unroll
+                        for (int w = 0; w < kFlowWarps; ++w)          // (all loads issued before the first compare)
+                            if (w < active_warps) key = max(key, keys[w * kWarp]);
 #pragma unroll
                         for (int off = 16; off > 0; off >>= 1) key = max(key, __shfl_xor_sync(kFullMask, key, off));
                         best = from_ordered_bits((unsigned)(key >> 32));
@@ -560,13 +568,14 @@ bool forward_flow_supported(const ForwardArgs &a) {
 }
 
 // Estimated seconds, from B200 measurements (profiles/r02_flow_kernel.txt; one sequence, us per step):
-// S = 640: 2.19, 1440: 2.81 -- against 2.6 / 3.2 for the wide kernel -- but 4.4 at 2048, 13 at 4096 (rows
-// beyond the registers) and 5.4 at 256 (two busy warps per CTA).  Sequences run one after the other.
+// S = 640: 2.02, 1440: 2.53, 2048: 3.29 -- against 2.6 / 3.2 / 3.9 for the wide kernel -- but 13 at 4096 (rows
+// beyond the registers) and 4.4 at 256 (two busy warps per CTA).  Sequences run one after the other.
 double flow_estimate_seconds(const int32_t *frames_sorted, int64_t B, int64_t S, int sm_count) {
     const FlowGeometry g = flow_geometry(S, sm_count);
     double step_us;
-    if (S < 512) step_us = 5.5;
-    else if (g.direct && S <= 1536) step_us = 1.69 + 0.00078 * (double)S;
+    if (S < 512) step_us = 4.4;
+    else if (g.direct && S <= 1536) step_us = 1.55 + 0.00068 * (double)S;
+    else if (g.direct) step_us = 3.3;
     else if (g.KQ == 1) step_us = 1.0 + 0.0017 * (double)S;
     else step_us = 2.0 + 0.0027 * (double)S * g.KQ * g.KQ / 4.0 + 0.6 * std::max(0, g.R - g.RR - g.smem_rows);
     double total = 0.0;
@@ -623,12 +632,13 @@ cudaError_t launch_forward_flow(const ForwardArgs &a, cudaStream_t stream) {
         // cooperative: every CTA polls every other CTA's stores, so all must be co-resident
         return cudaLaunchCooperativeKernel((void *)kernel, dim3(g.NC), dim3(kFlowThreads), args, g.smem, stream);
     };
-    if (g.KQ == 1 && g.RR == 4) return launch(forward_flow_kernel<1, 4>);
-    if (g.KQ == 1 && g.RR == 10) return launch(forward_flow_kernel<1, 10>);
-    if (g.KQ == 1) return launch(forward_flow_kernel<1, 20>);
-    if (g.KQ == 2) return launch(forward_flow_kernel<2, 8>);
-    if (g.KQ == 4) return launch(forward_flow_kernel<4, 3>);
-    return launch(forward_flow_kernel<8, 1>);
+    const bool all_reg = g.R <= g.RR;
+    if (g.KQ == 1 && g.RR == 4) return all_reg ? launch(forward_flow_kernel<1, 4, true>) : launch(forward_flow_kernel<1, 4, false>);
+    if (g.KQ == 1 && g.RR == 10) return all_reg ? launch(forward_flow_kernel<1, 10, true>) : launch(forward_flow_kernel<1, 10, false>);
+    if (g.KQ == 1) return all_reg ? launch(forward_flow_kernel<1, 20, true>) : launch(forward_flow_kernel<1, 20, false>);
+    if (g.KQ == 2) return launch(forward_flow_kernel<2, 8, false>);
+    if (g.KQ == 4) return launch(forward_flow_kernel<4, 3, false>);
+    return launch(forward_flow_kernel<8, 1, false>);
 }
 
 }  // namespace torbi_b200
