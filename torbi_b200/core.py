@@ -549,9 +549,17 @@ def _from_files_native(input_files, sizes, mapping, transition, initial, log_pro
         numel = max(sum(int(sizes[i]) for i in batch) for batch in batches) // 4 + 1
     else:
         numel = max(len(batch) * int(sizes[batch[0]]) for batch in batches) // 4 + 1
+    if packed and sum(int(size) for size in sizes) >= batch_bytes:
+        numel = max(numel, batch_bytes // 4 + 1)      # one ring-buffer size for every large call: the kept buffers fit
     pin = torch.cuda.is_available()
     free: queue.Queue = queue.Queue()
+    timing = os.environ.get('TORBI_B200_PIPELINE_TIMING') == '1'
+    import time as _time
+    t_start = _time.perf_counter()
     ring = _take_pinned_buffers(depth + 1, numel, pin)
+    if timing:
+        print(f'pipeline: {len(input_files)} files, {len(batches)} batches, ring of {depth + 1} x {numel * 4 >> 20} MB '
+              f'ready after {_time.perf_counter() - t_start:.3f} s', flush=True)
     for buffer in ring:
         free.put(buffer)
     ready: queue.Queue = queue.Queue(maxsize=depth)
@@ -616,6 +624,9 @@ def _from_files_native(input_files, sizes, mapping, transition, initial, log_pro
             if isinstance(item, BaseException):
                 raise item
             (observation, item_row, batch_frames, batch_chunks), files, buffer = item
+            if timing:
+                print(f'pipeline: batch of {len(files)} files ({observation.numel() * observation.element_size() >> 20} MB) '
+                      f'loaded at {_time.perf_counter() - t_start:.3f} s', flush=True)
             use_banded = (banded and len(files) >= 32) if banded is not None else None
             if item_row is not None:
                 indices = _from_probabilities_packed(
@@ -645,8 +656,12 @@ def _from_files_native(input_files, sizes, mapping, transition, initial, log_pro
                                         io_threads))
             if bar is not None:
                 bar.update(len(files))
+        if timing:
+            print(f'pipeline: last batch decoded at {_time.perf_counter() - t_start:.3f} s', flush=True)
         for future in pending:
             future.result()
+        if timing:
+            print(f'pipeline: last file written at {_time.perf_counter() - t_start:.3f} s', flush=True)
     finally:
         # a failed decode / save must not leave the loader thread blocked on a full queue holding
         # pinned batch buffers: tell it to stop, then wait for it
