@@ -373,7 +373,7 @@ def other_configs(lib, device, local, peaks, sm_count, barrier, args):
             clk = peaks['sm_max_mhz'] * 1e6
             ldp = -(-S // 96) * 96
             rows = -(-S // sm_count)
-            resident = min(rows, (200 * 1024 - 4 * ldp) // (4 * ldp))
+            resident = min(rows, (226 * 1024 - 4 * ldp) // (4 * ldp))
             streamed_bytes = (rows - resident) * ldp * 4.0 * -(-S // rows)
             floor_us = 1.25 + 1e6 * max(S * S / sm_count / 64.0 / clk, streamed_bytes / 13.7e12)
             us = 1e3 * r['fwd_ms'] / max(1, timesteps - 1)

@@ -280,7 +280,7 @@ WideGeometry wide_geometry(int64_t B, int64_t S, int sm_count) {
     g.R = (int)((S + sm_count - 1) / sm_count);
     g.NC = (int)((S + g.R - 1) / g.R);
     const size_t ldp = (size_t)padded_sources(S);
-    const size_t slice = sizeof(float) * g.R * ldp, budget = 200 * 1024;
+    const size_t slice = sizeof(float) * g.R * ldp, budget = 226 * 1024;   // (227 KB per CTA minus the static arrays)
     // as many sequences in lockstep as the batch has and shared memory holds
     g.BC = B > 8 ? 16 : B > 4 ? 8 : B > 2 ? 4 : B > 1 ? 2 : 1;
     while (g.BC > 1 && sizeof(float) * g.BC * ldp > budget) g.BC /= 2;
@@ -296,7 +296,7 @@ WideGeometry wide_geometry(int64_t B, int64_t S, int sm_count) {
 
 bool forward_wide_supported(const ForwardArgs &a) {
     const WideGeometry g = wide_geometry(a.B, a.S, a.sm_count);
-    return g.smem <= 200 * 1024 && a.ws.transition_pad != nullptr;
+    return g.smem <= 226 * 1024 && a.ws.transition_pad != nullptr;
 }
 
 // Estimated seconds for the wide kernel: per step a fixed exchange + barrier cost
