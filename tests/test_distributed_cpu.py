@@ -43,6 +43,31 @@ def _worker(rank, world_size, port, result_file):
         assert sorted(sum(everyone, [])) == list(range(B))   # a partition of the batch
         loads = [int(frames[it].sum()) for it in everyone]
         assert max(loads) <= 0.65 * int(frames.sum())         # balanced by length
+        # files of a corpus dealt by size: a partition, balanced, the same on every rank without a message;
+        # the per-rank driver hands exactly that share to from_files_to_files
+        import pathlib
+        import torbi_b200
+        root = pathlib.Path(result_file).parent
+        inputs, outputs = [], []
+        for i, n in enumerate([40, 3, 17, 25, 9, 31, 2]):
+            inputs.append(root / f'in{i}.pt')
+            outputs.append(root / f'out{i}.pt')
+            if rank == 0:
+                torch.save(torch.zeros(n, 8), inputs[-1])
+        dist.barrier()
+        mine_in, mine_out = distributed.shard_files(inputs, outputs)
+        shares = [None] * world_size
+        dist.all_gather_object(shares, [str(f) for f in mine_in])
+        assert sorted(sum(shares, [])) == sorted(str(f) for f in inputs)
+        assert [f.name.replace('in', 'out') for f in mine_in] == [f.name for f in mine_out]
+        seen = []
+        original = torbi_b200.from_files_to_files
+        torbi_b200.from_files_to_files = lambda i, o, *a, **k: seen.append((list(i), list(o), k.get('gpu')))
+        try:
+            distributed.from_files_to_files(inputs, outputs, log_probs=True, gpu=rank)
+        finally:
+            torbi_b200.from_files_to_files = original
+        assert seen == [(mine_in, mine_out, rank)]
         if rank == 0:
             with open(result_file, 'w') as f:
                 f.write('ok')
