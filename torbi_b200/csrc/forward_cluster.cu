@@ -73,7 +73,7 @@ struct ClusterParams {
 size_t cluster_smem_bytes(int ldp) {
     return sizeof(float) * (kWarps * kSlots * kSlotFloats + TN * (ldp / 2 + 4)) +
            sizeof(float4) * (2 * kWarps * kReduceThreads + 2 * kReduceThreads) +
-           sizeof(int) * (6 * kMaxBatches * TM + kMaxBatches) + sizeof(u64) * 2 + 16;
+           sizeof(int) * (6 * kMaxBatches * TM + kMaxBatches + 1) + sizeof(u64) * 6 + 16;
 }
 
 __device__ __forceinline__ u64 add2(u64 a, u64 b) {     // two fp32 adds (FADD2), IEEE rn
@@ -170,14 +170,29 @@ __device__ __forceinline__ void group_barrier(unsigned *counter, unsigned target
 
 #ifdef TORBI_TILED_PROFILE
 #define CPROF_DECL long long prof_t0 = clock64(), prof_acc[6] = {0, 0, 0, 0, 0, 0}; long long prof_steps = 0;
+#define CPROF_REDUCER_PRINT                                                                                              \
+    if (lane == 0 && blockIdx.x % 37 == 0 && warp == kWarps && prof_steps > 0)                                           \
+        printf("cta %d reducer warp batch-steps %lld cycles/batch-step: emission requests %lld, wait for the partials %lld, " \
+               "8-way maximum %lld, DSMEM exchange + publish %lld, fence + counter %lld\n", blockIdx.x, prof_steps,         \
+               prof_acc[3] / prof_steps, prof_acc[4] / prof_steps, prof_acc[5] / prof_steps, prof_acc[0] / prof_steps,     \
+               prof_acc[1] / prof_steps);
 #define CPROF_MARK(i) { const long long prof_now = clock64(); prof_acc[i] += prof_now - prof_t0; prof_t0 = prof_now; }
 #else
 #define CPROF_DECL
+#define CPROF_REDUCER_PRINT
 #define CPROF_MARK(i)
 #endif
 
-template <uint32_t kFlags>
-__global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const ClusterParams p) {
+// kWS (warp specialised): a ninth warp does everything after the K loop -- it collects the eight warps' partial
+// maxima (handed over through double-buffered shared memory and mbarriers), runs the DSMEM exchange with the
+// peer CTA, adds the emissions, publishes and signals the batch's counter -- while the eight K-loop warps go
+// straight on to the next batch of the group.  Without it warps 0..4 carry that tail themselves (5.6 k of
+// 15.1 k cycles per batch-step, profiles/r02_ab_cluster_vs_split.txt) and the other three idle behind them.
+// Measured: bit-exact, but slower still -- one warp sharing a scheduler with two K-loop warps takes ~12 k
+// cycles for the tail (same file), so it is off by default (TORBI_B200_CLUSTER_WS=1 selects it).
+template <uint32_t kFlags, bool kWS>
+__global__ void __launch_bounds__(kWS ? kThreads + kWarp : kThreads, 1) forward_cluster_kernel(const ClusterParams p) {
+    constexpr int kAllThreads = kWS ? kThreads + kWarp : kThreads;
     extern __shared__ __align__(16) float smem[];
     const int S = p.S, LDP = p.LDP;
     const int KH4 = LDP / 2;                                    // sources of this CTA's half
@@ -191,7 +206,9 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
     int *s_item = reinterpret_cast<int *>(s_hrow + kMaxBatches * TM);    // [kMaxBatches][TM]
     int *s_frames = s_item + kMaxBatches * TM;                  // [kMaxBatches][TM]
     int *s_len = s_frames + kMaxBatches * TM;                   // [kMaxBatches] frames of the batch's longest item
-    u64 *inbox_bar = reinterpret_cast<u64 *>(s_len + kMaxBatches);   // [2]
+    u64 *inbox_bar = reinterpret_cast<u64 *>(s_len + kMaxBatches + (kMaxBatches & 1));   // [2]
+    u64 *part_full = inbox_bar + 2;                             // [2] kWS: the eight warps' partials of a batch-step are in
+    u64 *part_empty = part_full + 2;                            // [2] kWS: ... and have been read by the ninth warp
 
     const int tid = threadIdx.x, lane = tid % kWarp, warp = tid / kWarp;
     const int lane_b = lane / LANES_J, lane_j = lane % LANES_J;
@@ -202,12 +219,17 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
     const unsigned group_ctas = 2u * p.NJT;
 
     if (tid == 0) {
-        mbar_init(inbox_bar + 0, kReduceThreads / 2);
-        mbar_init(inbox_bar + 1, kReduceThreads / 2);
+        // arrivals per phase: one per pushing thread (80), or one per pushing LANE of the ninth warp (16)
+        mbar_init(inbox_bar + 0, kWS ? kWarp / 2 : kReduceThreads / 2);
+        mbar_init(inbox_bar + 1, kWS ? kWarp / 2 : kReduceThreads / 2);
+        for (int k = 0; k < 2; ++k) {
+            mbar_init(part_full + k, kWarps);
+            mbar_init(part_empty + k, 1);
+        }
         mbar_fence_init();
     }
     // the pair's half of the transition block, once per launch
-    for (int idx = tid; idx < TN * (KH4 / 4); idx += kThreads) {
+    for (int idx = tid; idx < TN * (KH4 / 4); idx += kAllThreads) {
         const int r = idx / (KH4 / 4), q = idx % (KH4 / 4);
         *reinterpret_cast<float4 *>(A_res + r * LDA + q * 4) =
             __ldg(reinterpret_cast<const float4 *>(p.transition + (int64_t)(j0 + r) * LDP + rank * KH4) + q);
@@ -216,11 +238,12 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
     if (group >= p.NG) return;     // (never: the grid is NG * NJT clusters)
 
     // this warp's share of the CTA's sources, in k-steps (float4 groups)
+    const bool compute_warp = warp < kWarps;                    // (kWS: warp 8 is the reducer)
     int kofs = 0;
-    for (int w = 0; w < warp; ++w) kofs += p.nk[w];
-    const int nk = p.nk[warp];
+    for (int w = 0; w < min(warp, kWarps); ++w) kofs += p.nk[w];
+    const int nk = compute_warp ? p.nk[warp] : 0;
     const int ns = (nk + kStageSteps - 1) / kStageSteps;        // ring stages per batch-step
-    float *wring = ring + warp * (kSlots * kSlotFloats);
+    float *wring = ring + min(warp, kWarps - 1) * (kSlots * kSlotFloats);
     const int ld_chunk = (lane % 8) * 4, ld_row = lane / 8;     // cp.async mapping: 16-byte column, rows ld_row + 4 q
     const int64_t src_col0 = (int64_t)rank * KH4 + kofs * 4;    // first source column of this warp
     const float *Aw = A_res + lane_j * LDA + kofs * 4;
@@ -228,8 +251,9 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
     // ownership of the reduced tile: slot u = quad * 32 + lane of the compute mapping; the pair member
     // whose rank equals the parity of lane_b finalises it (all four lanes of a column group agree)
     const int u_quad = tid / kWarp, u_lane = lane;
-    const bool reducer = tid < kReduceThreads;
-    const bool mine = reducer && (((u_lane >> 2) & 1) == (int)rank);
+    const bool reducer = !kWS && tid < kReduceThreads;
+    const bool mine_lane = ((u_lane >> 2) & 1) == (int)rank;
+    const bool mine = reducer && mine_lane;
     // after the 4 x 4 transpose an owner holds element e = 4 quad + lane_j of lanes lane_j' = 0..3:
     // row lane_b + 8 (e / 5), columns 4 (e % 5) .. + 3 of the tile
     const int fin_e = 4 * u_quad + lane_j;
@@ -255,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
         const int batches = min(kMaxBatches, group_batches - wave0);
         auto global_batch = [&](int b) { return group + p.NG * (wave0 + b); };
         __syncthreads();
-        for (int idx = tid; idx < batches * TM; idx += kThreads) {
+        for (int idx = tid; idx < batches * TM; idx += kAllThreads) {
             const int item = p.order[(int64_t)global_batch(idx / TM) * TM + idx % TM];
             s_item[idx] = item;
             s_frames[idx] = item >= 0 ? p.frames[item] : 0;
@@ -271,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
         {
             const int c_end = (jt == p.NJT - 1) ? LDP : min(j0 + TN, LDP);
             const int cols = c_end - j0;
-            for (int idx = tid; idx < batches * (TM / 2) * cols; idx += kThreads) {
+            for (int idx = tid; idx < batches * (TM / 2) * cols; idx += kAllThreads) {
                 const int c = j0 + idx % cols, rr = idx / cols;
                 const int b = rr / (TM / 2), r = rank * (TM / 2) + rr % (TM / 2);
                 const int item = s_item[b * TM + r];
@@ -332,6 +356,108 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
         };
 
         CPROF_DECL
+        if (kWS && !compute_warp) {
+            // ================= the ninth warp: reduce, exchange, publish =================
+            Cursor rc;
+            cursor_first(rc, s_len, batches);
+            while (rc.n > 0) {
+                const int b = rc.b, tau = rc.tau;
+                const int64_t row0 = (int64_t)global_batch(b) * TM;
+                // emissions of the cells this lane finalises (one float4 per quad), requested before the wait
+                float4 emit[kQuads];
+                bool live[kQuads];
+                int64_t hrow[kQuads];
+#pragma unroll
+                for (int q = 0; q < kQuads; ++q) {
+                    const int e = 4 * q + lane_j;
+                    const int frow = lane_b + LANES_B * (e / N), fcol = 4 * (e % N);
+                    const int item = mine_lane ? s_item[b * TM + frow] : -1;
+                    live[q] = mine_lane && item >= 0 && tau < s_frames[b * TM + frow] && j0 + fcol < S;
+                    hrow[q] = mine_lane ? s_hrow[b * TM + frow] : 0;
+                    emit[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live[q]) {
+                        if (p.frames_ready) wait_for_frame(tau);
+                        const int64_t e0 = (s_row[b * TM + frow] + tau) * S + j0 + fcol;
+                        if (obs_vec) {
+                            emit[q] = __ldcg(reinterpret_cast<const float4 *>(p.observation + e0));
+                        } else {
+                            emit[q].x = load_observation(p.observation, e0, p.obs_dtype);
+                            if (j0 + fcol + 1 < S) emit[q].y = load_observation(p.observation, e0 + 1, p.obs_dtype);
+                            if (j0 + fcol + 2 < S) emit[q].z = load_observation(p.observation, e0 + 2, p.obs_dtype);
+                            if (j0 + fcol + 3 < S) emit[q].w = load_observation(p.observation, e0 + 3, p.obs_dtype);
+                        }
+                    }
+                }
+                const unsigned par = reduce_count & 1u, phase = (reduce_count >> 1) & 1u;
+                CPROF_MARK(3)
+                mbar_wait(part_full + par, phase);                  // the eight warps' partials are in
+                CPROF_MARK(4)
+                float4 m[kQuads];
+#pragma unroll
+                for (int q = 0; q < kQuads; ++q) {
+                    const float4 *col = partial + par * kWarps * kReduceThreads + q * kWarp + lane;
+                    m[q] = col[0];
+#pragma unroll
+                    for (int w = 1; w < kWarps; ++w) m[q] = max4(m[q], col[w * kReduceThreads]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(part_empty + par);       // the buffer may be refilled
+                CPROF_MARK(5)
+                if (!mine_lane) {
+#pragma unroll
+                    for (int q = 0; q < kQuads; ++q)
+                        st_cluster_f4(map_to_rank(smem_u32(inbox + par * kReduceThreads + q * kWarp + lane), peer), m[q]);
+                    mbar_arrive_remote(map_to_rank(smem_u32(inbox_bar + par), peer));
+                } else {
+                    mbar_wait_cluster(inbox_bar + par, phase);
+#pragma unroll
+                    for (int q = 0; q < kQuads; ++q) {
+                        float4 v = max4(m[q], inbox[par * kReduceThreads + q * kWarp + lane]);
+                        // 4 x 4 transpose across the column group (see the 256-thread path below)
+                        float s0 = (lane_j & 1) ? v.x : v.y, s1 = (lane_j & 1) ? v.z : v.w;
+                        s0 = __shfl_xor_sync(fin_mask, s0, 1);
+                        s1 = __shfl_xor_sync(fin_mask, s1, 1);
+                        if (lane_j & 1) { v.x = s0; v.z = s1; } else { v.y = s0; v.w = s1; }
+                        float t0 = (lane_j & 2) ? v.x : v.z, t1 = (lane_j & 2) ? v.y : v.w;
+                        t0 = __shfl_xor_sync(fin_mask, t0, 2);
+                        t1 = __shfl_xor_sync(fin_mask, t1, 2);
+                        if (lane_j & 2) { v.x = t0; v.y = t1; } else { v.z = t0; v.w = t1; }
+                        if (live[q]) {
+                            const int e = 4 * q + lane_j;
+                            const int frow = lane_b + LANES_B * (e / N), col0 = j0 + 4 * (e % N);
+                            float4 o;
+                            o.x = convert_observation<kFlags>(emit[q].x) + v.x;
+                            o.y = convert_observation<kFlags>(emit[q].y) + v.y;
+                            o.z = convert_observation<kFlags>(emit[q].z) + v.z;
+                            o.w = convert_observation<kFlags>(emit[q].w) + v.w;
+                            float *dst = p.score0 + (tau & 1) * p.score_stride + (row0 + frow) * LDP + col0;
+                            float *hist = p.history + (hrow[q] + tau) * S + col0;
+                            if (col0 + 3 < S) {
+                                *reinterpret_cast<float4 *>(dst) = o;
+                                if (hist_vec) __stcs(reinterpret_cast<float4 *>(hist), o);
+                                else { hist[0] = o.x; hist[1] = o.y; hist[2] = o.z; hist[3] = o.w; }
+                            } else {
+                                const float ee[4] = {o.x, o.y, o.z, o.w};
+                                for (int x = 0; col0 + x < S; ++x) { dst[x] = ee[x]; hist[x] = ee[x]; }
+                            }
+                        }
+                    }
+                }
+                // one arrival per CTA on the batch's publish counter, after all of its stores
+                __syncwarp();
+                CPROF_MARK(0)
+                if (lane == 0) {
+                    __threadfence();
+                    atomicAdd(p.sync + (size_t)kSyncStride * (1 + global_batch(b)), 1u);
+                }
+                CPROF_MARK(1)
+                ++reduce_count;
+                cursor_next(rc, s_len);
+#ifdef TORBI_TILED_PROFILE
+                ++prof_steps;
+#endif
+            }
+        } else
         while (cc.n > 0) {
             const int b = cc.b, tau = cc.tau;
             const int64_t row0 = (int64_t)global_batch(b) * TM;
@@ -402,6 +528,8 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
             // ---- the 16 partial maxima of every cell meet: 8 warps through shared memory ... ----
             const unsigned par = reduce_count & 1u;
             float4 *my_partial = partial + (par * kWarps + warp) * kReduceThreads;
+            if (kWS && reduce_count >= 2)                       // the ninth warp has read what this buffer held
+                mbar_wait(part_empty + par, ((reduce_count >> 1) - 1u) & 1u);
 #pragma unroll
             for (int q = 0; q < kQuads; ++q) {
                 // element e = i * N + c of the thread's tile; quad q holds e = 4 q .. 4 q + 3
@@ -410,7 +538,12 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
                 for (int x = 0; x < 4; ++x) v[x] = cur[(4 * q + x) / N][(4 * q + x) % N];
                 my_partial[q * kWarp + lane] = make_float4(v[0], v[1], v[2], v[3]);
             }
-            __syncthreads();
+            if constexpr (kWS) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(part_full + par);    // (release: the partials are visible to the waiter)
+            } else {
+                __syncthreads();
+            }
             CPROF_MARK(1)
             if (reducer) {
                 const float4 *col = partial + par * kWarps * kReduceThreads + tid;
@@ -471,6 +604,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
 #endif
         }
         cp_async_wait_all();
+        CPROF_REDUCER_PRINT
 #ifdef TORBI_TILED_PROFILE
         if (lane == 0 && blockIdx.x % 37 == 0 && (warp == 0 || warp == 7) && prof_steps > 0)
             printf("cta %d warp %d batch-steps %lld cycles/batch-step: K loop %lld, partial store + CTA barrier %lld, reduce + DSMEM + publish %lld\n",
@@ -481,7 +615,8 @@ __global__ void __launch_bounds__(kThreads, 1) forward_cluster_kernel(const Clus
         group_target += group_ctas;
         group_barrier(group_counter, group_target);
         const int cta_in_group = jt * 2 + (int)rank;
-        for (int rr = cta_in_group * kWarps + warp; rr < batches * TM; rr += (int)group_ctas * kWarps) {
+        constexpr int kAllWarps = kAllThreads / kWarp;
+        for (int rr = cta_in_group * kAllWarps + warp; rr < batches * TM; rr += (int)group_ctas * kAllWarps) {
             const int item = s_item[rr];
             if (item < 0) continue;
             const int b = rr / TM, r = rr % TM;
@@ -585,7 +720,11 @@ cudaError_t launch_forward_cluster(const ForwardArgs &a, cudaStream_t stream) {
     p.NJT = cluster_njt(a.S);
     p.num_batches = (int)((a.B + TM - 1) / TM);
     p.NG = std::min(a.sm_count / 2 / p.NJT, p.num_batches);
-    int bonus = 1;
+    // TORBI_B200_CLUSTER_WS=1: ninth (reducer) warp.  Measured slower than the 256-thread kernel (3.32 M vs 3.81 M
+    // timesteps/s at 64 sequences): the single reducing warp needs ~12 k cycles per batch-step -- more than a K loop
+    bool ws = false;
+    if (const char *env = std::getenv("TORBI_B200_CLUSTER_WS")) ws = std::atoi(env) != 0;
+    int bonus = ws ? 0 : 1;
     if (const char *env = std::getenv("TORBI_B200_CLUSTER_BONUS")) bonus = std::max(0, std::min(8, std::atoi(env)));
     split_k_steps(p.LDP / 8, bonus, p.nk);
 
@@ -597,7 +736,7 @@ cudaError_t launch_forward_cluster(const ForwardArgs &a, cudaStream_t stream) {
         if (err != cudaSuccess) return err;
         cudaLaunchConfig_t config{};
         config.gridDim = dim3(2 * p.NG * p.NJT);
-        config.blockDim = dim3(kThreads);
+        config.blockDim = dim3(ws ? kThreads + kWarp : kThreads);
         config.dynamicSmemBytes = smem;
         config.stream = stream;
         cudaLaunchAttribute attrs[2];
@@ -615,10 +754,10 @@ cudaError_t launch_forward_cluster(const ForwardArgs &a, cudaStream_t stream) {
         return cudaLaunchKernelExC(&config, (const void *)kernel, args);
     };
     switch (a.flags & 3u) {
-        case 0: return launch(forward_cluster_kernel<0>);
-        case 1: return launch(forward_cluster_kernel<1>);
-        case 2: return launch(forward_cluster_kernel<2>);
-        default: return launch(forward_cluster_kernel<3>);
+        case 0: return ws ? launch(forward_cluster_kernel<0, true>) : launch(forward_cluster_kernel<0, false>);
+        case 1: return ws ? launch(forward_cluster_kernel<1, true>) : launch(forward_cluster_kernel<1, false>);
+        case 2: return ws ? launch(forward_cluster_kernel<2, true>) : launch(forward_cluster_kernel<2, false>);
+        default: return ws ? launch(forward_cluster_kernel<3, true>) : launch(forward_cluster_kernel<3, false>);
     }
 }
 
