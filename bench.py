@@ -91,8 +91,10 @@ def measured_peaks():
 def profiled_traffic(kernel, args, backtrace='backtrace_recompute'):
     """DRAM bytes (read + write) of one launch of the forward kernel from the
     committed `ncu --set full` capture of this same workload, or None."""
-    path = ROOT / 'profiles' / ('forward_tiled_hist_ncu_full.json' if backtrace == 'backtrace_recompute'
+    path = ROOT / 'profiles' / ('r02_forward_tiled_hist_ncu_full.json' if backtrace == 'backtrace_recompute'
                                 else 'forward_tiled_ncu_full.json')
+    if not path.exists():
+        path = ROOT / 'profiles' / 'forward_tiled_hist_ncu_full.json'
     if kernel != 'forward_tiled' or not path.exists() or \
             (args.batch, args.frames, args.states) != (512, 2000, 1440):
         return None
