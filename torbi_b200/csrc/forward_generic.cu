@@ -57,7 +57,8 @@ forward_generic_kernel(const float *__restrict__ observation, int obs_dtype,
         for (int j = warp; j < S; j += nwarps) {
             const float *row = transition + (int64_t)j * S;
             float emit = 0.f;
-            if (lane == 0) emit = convert_observation<kFlags>(load_observation(observation, obs_t + j, obs_dtype));
+            // (raw: converted where it is added, so the warp does not wait for the load before its scan)
+            if (lane == 0) emit = load_observation(observation, obs_t + j, obs_dtype);
             float best = -INFINITY;
             int arg = 0x7fffffff;
             bool any = false;
@@ -89,9 +90,10 @@ forward_generic_kernel(const float *__restrict__ observation, int obs_dtype,
                 if (better(ov, oi, best, arg)) { best = ov; arg = oi; }
             }
             if (lane == 0) {
+                const float score = convert_observation<kFlags>(emit) + best;
                 bp_t[j] = static_cast<uint16_t>(arg);
-                nxt[j] = emit + best;
-                if (ck) ck[j] = emit + best;
+                nxt[j] = score;
+                if (ck) ck[j] = score;
             }
         }
         float *tmp = cur; cur = nxt; nxt = tmp;
