@@ -82,7 +82,7 @@ extern "C" {
  * hence the same result bit for bit.  With this flag the kernel tracks the argmax of every state
  * and stores uint16 backpointers (2 bytes per (b,t,s)) like the reference's trellis
  * (viterbi.cpp:91-104); slower, half the workspace.  Pass the same flag to
- * torbi_b200_workspace_bytes.  The wide and generic kernels always store backpointers. */
+ * torbi_b200_workspace_bytes.  The wide, flow and generic kernels always store backpointers. */
 #define TORBI_B200_BACKPOINTERS (1u << 16)
 /* force the split-K small-tile kernel (32 sequences x 20 states per CTA with the transition block
  * resident in shared memory, or 16 x 40 streamed; score-history mode): the decomposition for batches
@@ -113,10 +113,11 @@ TORBI_B200_API const char *torbi_b200_last_error(void);
 /* Number of CUDA devices usable by this library (compute capability 10.x). */
 TORBI_B200_API int torbi_b200_device_count(void);
 
-/* Bytes of device workspace torbi_b200_decode needs for this shape
+/* Upper bound of the device workspace torbi_b200_decode needs for this shape, whatever the lengths
  * (fp32 score history B*T*S*4 -- or uint16 backpointers B*T*S*2 with
- * TORBI_B200_BACKPOINTERS --, rotating forward scores, scheduling state).
- * Returns 0 on invalid shape. */
+ * TORBI_B200_BACKPOINTERS --, rotating forward scores, scheduling state).  The history / backpointers
+ * only ever hold the frames that exist (sum of batch_frames rows): torbi_b200_workspace_bytes_planned
+ * gives the exact figure for one call.  Returns 0 on invalid shape. */
 TORBI_B200_API size_t torbi_b200_workspace_bytes(int64_t batch, int64_t frames, int64_t states, uint32_t flags);
 
 /* The same for one concrete call: the library picks the forward kernel from the length profile first
