@@ -528,6 +528,183 @@ __global__ void __launch_bounds__(kFlowThreads, 1) forward_flow_kernel(const Flo
     }
 }
 
+// ---------------------------------------------------------------------------
+// The same recursion for the shapes that matter most to it (config 1: 1440 states): one float4 source group per
+// thread (S <= 2048) and every transition row of the CTA in registers.  A dedicated, branch-free step: the general
+// kernel above spends ~680 instructions per warp and step of which 40 are the max-plus math -- the rest is index
+// arithmetic, predication and divergence bookkeeping of its register / shared-memory / streamed row paths (ncu
+// source view of profiles/r02_forward_flow_ncu_full.json: IMAD 1408, ISETP 1143, SEL 792, BRA 691, BSSY + BSYNC 816
+// against FADD2 240 per CTA and step).  Here a thread computes its RR candidates unconditionally (rows the CTA does
+// not own hold -inf), stores one 64-bit key per row -- (order-preserving score bits << 32) | ~source, so an integer
+// maximum is (score desc, source asc) -- and after the ONE CTA barrier the warp that owns a row reduces its 512 keys.
+// ---------------------------------------------------------------------------
+template <int RR>
+__global__ void __launch_bounds__(kFlowThreads, 1) forward_flow_direct_kernel(const FlowParams p) {
+    extern __shared__ __align__(16) unsigned flow_smem[];
+    u64 *cand = reinterpret_cast<u64 *>(flow_smem);               // [2][RR][kFlowThreads] candidate keys
+    __shared__ float red_val[kFlowWarps];
+    __shared__ int red_idx[kFlowWarps];
+    constexpr int kRounds = (RR + kFlowWarps - 1) / kFlowWarps;   // rows a warp finalises
+
+    const int S = p.S, LDP = p.LDP, R = p.R;
+    const int tid = threadIdx.x, lane = tid % kWarp, warp = tid / kWarp;
+    const int j_begin = blockIdx.x * R;
+    const int rows = max(0, min(R, S - j_begin));
+    const int valid = max(0, min(4, S - 4 * tid));                // real states among this thread's four sources
+    const bool warp_active = 4 * (warp * kWarp) < S;              // (warps whose lanes own no source skip the scan)
+
+    ulonglong2 a_reg[RR];
+    const ulonglong2 minus_inf = make_ulonglong2(0xff800000ff800000ull, 0xff800000ff800000ull);
+#pragma unroll
+    for (int r = 0; r < RR; ++r) {
+        a_reg[r] = minus_inf;
+        if (r < rows && 4 * tid < LDP)
+            a_reg[r] = __ldg(reinterpret_cast<const ulonglong2 *>(p.transition + (int64_t)(j_begin + r) * LDP) + tid);
+    }
+    // keys of threads that never store (idle warps) stay 0: below every real key
+    for (int i = tid; i < 2 * RR * kFlowThreads; i += kFlowThreads) cand[i] = 0ull;
+    FPROF_DECL
+    __syncthreads();
+
+    unsigned base = 0, steps_done = 0;
+    for (int n = 0; n < p.B; ++n) {
+        const int item = p.order[n];
+        const int frames = p.frames[item];
+        const int64_t row0 = p.item_row[item];
+        const int64_t hrow0 = p.hist_row[item];
+        u64 *set = p.ll + (size_t)(n & 1) * 2 * LDP;
+
+        // ---- t = 0: P_0[j] = obs[0][j] + initial[j]   (viterbi.cpp:72-76), own destination states ----
+        if (tid < rows) {
+            const int j = j_begin + tid;
+            st_ll(set + j, convert_observation_rt(load_observation(p.observation, row0 * S + j, p.obs_dtype), p.flags) +
+                               p.initial[j], base);
+        }
+        float emit[kRounds];
+        auto fetch_emissions = [&](int t) {
+#pragma unroll
+            for (int i = 0; i < kRounds; ++i) {
+                const int r = warp + i * kFlowWarps;
+                if (lane == 0 && r < rows && t < frames) {
+                    emit[i] = load_observation(p.observation, (row0 + t) * S + j_begin + r, p.obs_dtype);
+                    if (t + kEmissionAhead < frames)
+                        prefetch_l2(static_cast<const char *>(p.observation) +
+                                    ((row0 + t + kEmissionAhead) * S + j_begin + r) * (p.obs_dtype == 0 ? 4 : 2));
+                }
+            }
+        };
+        fetch_emissions(1);
+
+        for (int t = 1; t < frames; ++t, ++steps_done) {
+            const u64 *cur = set + ((t - 1) & 1) * LDP;
+            u64 *nxt = set + (t & 1) * LDP;
+            const unsigned tag = base + (unsigned)(t - 1);
+            u64 *keys = cand + (size_t)(steps_done & 1u) * RR * kFlowThreads;
+            FPROF_MARK(4)
+            // gate: thread c < #CTAs waits for the first score CTA c publishes, then everyone loads once
+            if (tid < p.NC) {
+                const u64 *word = cur + (size_t)tid * R;
+                FLOW_WATCHDOG_DECL
+                for (;;) {
+                    const u64 w = ld_ll(word);
+                    if (tag_of(w) == tag) break;
+                    FLOW_WATCHDOG(w, -tid)
+                }
+            }
+            __syncthreads();
+            FPROF_MARK(5)
+            if (warp_active) {
+                ulonglong2 P = make_ulonglong2(0ull, 0ull);
+                if (valid > 0) {
+                    const float4 v = poll_group(cur, tid, valid, tag);
+                    P.x = ((u64)__float_as_uint(v.y) << 32) | __float_as_uint(v.x);
+                    P.y = ((u64)__float_as_uint(v.w) << 32) | __float_as_uint(v.z);
+                }
+                FPROF_MARK(0)
+                const unsigned not_source = ~(unsigned)(4 * tid);
+#pragma unroll
+                for (int r = 0; r < RR; ++r) {
+                    const u64 v01 = add2(P.x, a_reg[r].x), v23 = add2(P.y, a_reg[r].y);
+                    const float v0 = lo(v01), v1 = hi(v01), v2 = lo(v23), v3 = hi(v23);
+                    const float mk = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+                    // ~(4 tid + i) = ~(4 tid) - i; i = first of the four attaining the maximum (ascending, viterbi.cpp:94-101)
+                    const unsigned low = not_source - (v0 == mk ? 0u : v1 == mk ? 1u : v2 == mk ? 2u : 3u);
+                    keys[(size_t)r * kFlowThreads + tid] = ((u64)ordered_bits(mk) << 32) | low;
+                }
+                FPROF_MARK(1)
+            }
+            __syncthreads();        // the only other CTA barrier of a step
+
+#pragma unroll
+            for (int i = 0; i < kRounds; ++i) {
+                const int r = warp + i * kFlowWarps;
+                if (r < rows) {
+                    const u64 *col = keys + (size_t)r * kFlowThreads + lane;
+                    u64 k[kFlowWarps];
+#pragma unroll
+                    for (int w = 0; w < kFlowWarps; ++w) k[w] = col[w * kWarp];
+                    u64 key = k[0];
+#pragma unroll
+                    for (int w = 1; w < kFlowWarps; ++w) key = max(key, k[w]);
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) key = max(key, __shfl_xor_sync(kFullMask, key, off));
+                    const float best = from_ordered_bits((unsigned)(key >> 32));
+                    const int source = (int)~(unsigned)key;
+                    const int j = j_begin + r;
+                    const float v = convert_observation_rt(__shfl_sync(kFullMask, emit[i], 0), p.flags) + best;
+                    if (lane == 0) {
+                        st_ll(nxt + j, v, base + (unsigned)t);
+                        p.backptr[(hrow0 + t) * S + j] = (uint16_t)min(source, S - 1);
+                        if (p.checkpoints && t % p.checkpoint_every == 0)
+                            p.checkpoints[((int64_t)item * p.ck_rows + (t / p.checkpoint_every - 1)) * S + j] = v;
+                    }
+                }
+            }
+            fetch_emissions(t + 1);
+            FPROF_MARK(2)
+        }
+        FPROF_PRINT(max(frames - 1, 1))
+
+        // ---- every CTA waits for the final scores, one writes them out (as in the general kernel) ----
+        {
+            const u64 *fin = set + ((frames - 1) & 1) * LDP;
+            const unsigned tag = base + (unsigned)(frames - 1);
+            const bool writer = (int)blockIdx.x == n % p.NC;
+            float best = -INFINITY;
+            int best_i = 0x7fffffff;
+            if (valid > 0) {
+                const float4 v = poll_group(fin, tid, valid, tag);
+                if (writer) {
+                    const float e[4] = {v.x, v.y, v.z, v.w};
+                    for (int x = 0; x < valid; ++x) {
+                        const int s = 4 * tid + x;
+                        if (p.posterior) p.posterior[(int64_t)item * S + s] = e[x];
+                        if (better(e[x], s, best, best_i)) { best = e[x]; best_i = s; }
+                    }
+                }
+            }
+            __syncthreads();        // (orders the reuse of the buffer set, see the general kernel)
+            if (writer) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const float ov = __shfl_xor_sync(kFullMask, best, off);
+                    const int oi = __shfl_xor_sync(kFullMask, best_i, off);
+                    if (better(ov, oi, best, best_i)) { best = ov; best_i = oi; }
+                }
+                if (lane == 0) { red_val[warp] = best; red_idx[warp] = best_i; }
+                __syncthreads();
+                if (tid == 0) {
+                    for (int w = 1; w < kFlowWarps; ++w)
+                        if (better(red_val[w], red_idx[w], best, best_i)) { best = red_val[w]; best_i = red_idx[w]; }
+                    p.final_state[item] = (best_i == 0x7fffffff) ? 0 : best_i;
+                }
+                __syncthreads();
+            }
+        }
+        base += (unsigned)frames;
+    }
+}
+
 struct FlowGeometry {
     int NC, R, KQ, RR, smem_rows, direct;
     size_t smem;
@@ -568,14 +745,14 @@ bool forward_flow_supported(const ForwardArgs &a) {
 }
 
 // Estimated seconds, from B200 measurements (profiles/r02_flow_kernel.txt; one sequence, us per step):
-// S = 640: 2.02, 1440: 2.53, 2048: 3.29 -- against 2.6 / 3.2 / 3.9 for the wide kernel -- but 13 at 4096 (rows
+// S = 640: 2.02, 1440: 2.53, 2048: 2.82 -- against 2.6 / 3.2 / 3.9 for the wide kernel -- but 13 at 4096 (rows
 // beyond the registers) and 4.4 at 256 (two busy warps per CTA).  Sequences run one after the other.
 double flow_estimate_seconds(const int32_t *frames_sorted, int64_t B, int64_t S, int sm_count) {
     const FlowGeometry g = flow_geometry(S, sm_count);
     double step_us;
     if (S < 512) step_us = 4.4;
     else if (g.direct && S <= 1536) step_us = 1.55 + 0.00068 * (double)S;
-    else if (g.direct) step_us = 3.3;
+    else if (g.direct) step_us = 2.85;
     else if (g.KQ == 1) step_us = 1.0 + 0.0017 * (double)S;
     else step_us = 2.0 + 0.0027 * (double)S * g.KQ * g.KQ / 4.0 + 0.6 * std::max(0, g.R - g.RR - g.smem_rows);
     double total = 0.0;
@@ -633,6 +810,25 @@ cudaError_t launch_forward_flow(const ForwardArgs &a, cudaStream_t stream) {
         return cudaLaunchCooperativeKernel((void *)kernel, dim3(g.NC), dim3(kFlowThreads), args, g.smem, stream);
     };
     const bool all_reg = g.R <= g.RR;
+    // The dedicated kernel halves the instruction count (scan 1270 -> 620 cycles, key reduction + publish 2200 -> 1330)
+    // yet the step only gets shorter where a CTA owns more than 10 rows: S = 2048 3.24 -> 2.82 us, but S = 1440
+    // 2.52 -> 2.71 and S = 640 2.02 -> 2.15 us (the wait moves into the score loads: the gate opens on a producer's
+    // FIRST row and the others now trail it), profiles/r02_flow_kernel.txt.  So it serves RR = 20 only;
+    // TORBI_B200_FLOW_DIRECT_KERNEL=1 / 0 forces it on (where possible) / off.
+    const bool can_dedicate = p.direct && all_reg && p.replicas == 1 && p.gate && g.KQ == 1;
+    bool dedicated = can_dedicate && g.RR == 20;
+    if (const char *env = std::getenv("TORBI_B200_FLOW_DIRECT_KERNEL")) dedicated = can_dedicate && std::atoi(env) != 0;
+    if (dedicated) {
+        const size_t bytes = sizeof(u64) * 2 * g.RR * kFlowThreads;
+        auto launch_direct = [&](auto kernel) {
+            cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (err != cudaSuccess) return err;
+            return cudaLaunchCooperativeKernel((void *)kernel, dim3(g.NC), dim3(kFlowThreads), args, bytes, stream);
+        };
+        if (g.RR == 4) return launch_direct(forward_flow_direct_kernel<4>);
+        if (g.RR == 10) return launch_direct(forward_flow_direct_kernel<10>);
+        return launch_direct(forward_flow_direct_kernel<20>);
+    }
     if (g.KQ == 1 && g.RR == 4) return all_reg ? launch(forward_flow_kernel<1, 4, true>) : launch(forward_flow_kernel<1, 4, false>);
     if (g.KQ == 1 && g.RR == 10) return all_reg ? launch(forward_flow_kernel<1, 10, true>) : launch(forward_flow_kernel<1, 10, false>);
     if (g.KQ == 1) return all_reg ? launch(forward_flow_kernel<1, 20, true>) : launch(forward_flow_kernel<1, 20, false>);
