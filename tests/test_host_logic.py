@@ -176,6 +176,50 @@ def test_chunk_matches_reference_golden(name, golden):
         assert all(c.data_ptr() == x[b].data_ptr() for c, b in zip(chunks, [0] + expected))   # views
 
 
+def test_packed_batch_is_cut_into_the_reference_chunks(monkeypatch):
+    """Host logic of the packed route with MIN_CHUNK_SIZE: the files of a batch lie back to back in one buffer, the
+    low-entropy decision is taken for all frames at once, and every FILE is cut exactly where the reference's
+    chunk() would cut it alone (chunk.py:12-49) -- never across a file boundary.  The device pieces (entropy
+    kernel, decode) are stood in for on the CPU here; the GPU tests cover them."""
+    import importlib
+    from torbi_b200 import core
+    chunk_module = importlib.import_module('torbi_b200.chunk')
+    rng = np.random.default_rng(5)
+    files = []
+    for frames in (120, 7, 64, 1, 90):
+        logits = rng.standard_normal((frames, 24))
+        logits[rng.random(frames) < 0.6] *= 12.0
+        files.append(torch.from_numpy(cases.log_softmax(logits)))
+    frames = torch.tensor([f.shape[0] for f in files], dtype=torch.int32)
+    item_row = torch.zeros(len(files), dtype=torch.int64)
+    item_row[1:] = torch.cumsum(frames.to(torch.int64), 0)[:-1]
+    packed = torch.cat(files)
+    seen = {}
+
+    def fake_decode_packed(observation, rows, lengths, transition, initial, *, flags=0, **kwargs):
+        seen['rows'], seen['frames'], seen['flags'] = rows.tolist(), lengths.tolist(), flags
+        return torch.zeros(observation.shape[0], dtype=torch.int32)
+    monkeypatch.setattr(core, 'decode_packed', fake_decode_packed)
+    monkeypatch.setattr(chunk_module, 'low_entropy_frames_device',
+                        lambda observation, threshold, stats=None: chunk_module.entropy(observation.T) < threshold)
+    stats = {}
+    out = core._from_probabilities_packed(packed, item_row, frames, None, None, True, torch.device('cpu'),
+                                          min_chunk_size=8, entropy_threshold=0.5, stats=stats)
+    assert out.shape == (packed.shape[0],)
+    want_rows, want_frames = [], []
+    for row0, observation in zip(item_row.tolist(), files):
+        bounds = [0] + chunk_module.split(observation, 8, 0.5) + [observation.shape[0]]
+        want_rows += [row0 + b for b in bounds[:-1]]
+        want_frames += list(np.diff(bounds))
+    assert seen['rows'] == want_rows and seen['frames'] == want_frames
+    assert len(want_rows) > len(files) and stats['pieces'] == len(want_rows)
+    assert seen['flags'] & _ffi.EPS_FLOOR and not seen['flags'] & _ffi.OBS_IS_PROBABILITY
+    # without chunking the items go through unchanged; probabilities are flagged for the fused log
+    core._from_probabilities_packed(packed.exp(), item_row, frames, None, None, False, torch.device('cpu'))
+    assert seen['rows'] == item_row.tolist() and seen['frames'] == frames.tolist()
+    assert seen['flags'] & _ffi.OBS_IS_PROBABILITY
+
+
 def test_evaluation_runner_host_logic(tmp_path, monkeypatch):
     """evaluate.datasets (evaluate/core.py:14-123) with the decode stubbed out: corpus synthesis,
     partition bookkeeping, the un-chunked reference decode, RPA and real-time-factor reporting."""
